@@ -1,0 +1,179 @@
+/*
+ * slamfe.h -- C ABI of the B200-native visual front-end (libslamfe.so).
+ *
+ * This is the drop-in boundary for the data-parallel front-end of ywrt/slam-robot:
+ * image-pyramid construction, coarse-to-fine patch tracking with forward/backward
+ * validation, dense SSD window search, and 256-bit Hamming matching.  Plain pointers and
+ * sizes only; no C++ or torch types.  Every entry point names the reference interface it
+ * replaces (file:line into the reference tree).  There is NO CPU fallback: every call
+ * needs a CUDA device and fails with SFE_ERR_CUDA otherwise.
+ *
+ * Conventions
+ *   - Functions return 0 (SFE_SUCCESS) or an sfe_error; sfe_last_error(ctx) has the text.
+ *   - "_dev" variants take DEVICE pointers and only enqueue work on the context's stream
+ *     (no synchronisation); the plain variants take HOST pointers, copy in, run, copy out
+ *     and return after the results are in the caller's buffers.
+ *   - Points are interleaved float x,y pairs in pixel units of pyramid level 0, exactly the
+ *     cv::Point2f values the reference passes around (matcher.cpp:173).
+ *   - Per-feature status values are the reference's Status enum (hessian.h:48-52).
+ *   - A context is bound to one GPU and one stream; calls on one context are stream-ordered
+ *     and must not be issued from several host threads at once (the reference's Matcher is
+ *     single-threaded too, main.cpp:490).
+ */
+#ifndef SLAMFE_H_
+#define SLAMFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFE_MAX_LEVELS 12
+#define SFE_PATCH 13 /* kWindowSize, matcher.cpp:27 */
+
+typedef struct sfe_ctx sfe_ctx;
+typedef struct sfe_pyr sfe_pyr;
+
+typedef enum { SFE_SUCCESS = 0, SFE_ERR_INVALID = 1, SFE_ERR_CUDA = 2, SFE_ERR_NOMEM = 3 } sfe_error;
+
+/* hessian.h:48-52 / klt.h:53-57 / brute.h:28-32 */
+typedef enum { SFE_OK = 0, SFE_SMALL_DET = 1, SFE_OUT_OF_BOUNDS = 2 } sfe_status;
+
+/* which tracker's MakePyramid: hessian.h:95-126, klt.h:98-137, brute.h:59-80 */
+typedef enum { SFE_HESSIAN = 0, SFE_KLT = 1, SFE_BRUTE = 2 } sfe_flavor;
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Replaces the FeatureTracker constructor (matcher.cpp:304 -> hessian.h:11-30): builds the
+ * 13x13 weighting mask once and uploads it. */
+int sfe_create(int device, sfe_ctx** out);
+void sfe_destroy(sfe_ctx* ctx);
+const char* sfe_last_error(const sfe_ctx* ctx);
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*); NULL restores the
+ * context's own stream. */
+int sfe_set_stream(sfe_ctx* ctx, void* cuda_stream);
+int sfe_sync(sfe_ctx* ctx);
+/* Copies the 169 mask weights (hessian.h:11-30) to host memory. */
+int sfe_get_mask(sfe_ctx* ctx, float* mask169);
+/* Pinned host memory for the host-pointer entry points (optional; any host memory works). */
+int sfe_host_alloc(sfe_ctx* ctx, size_t bytes, void** out);
+int sfe_host_free(sfe_ctx* ctx, void* p);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t sfe_launch_count(const sfe_ctx* ctx);
+
+/* ---- pyramids ------------------------------------------------------------------------ */
+
+/* Storage for `batch` pyramids of `depth` levels of a w x h frame; level sizes follow
+ * ((w+1)/2,(h+1)/2) (hessian.h:108).  Replaces the Pyramid = vector<GradImage> value type
+ * (hessian.h:42-46). */
+int sfe_pyr_create(sfe_ctx* ctx, int w, int h, int depth, int flavor, int batch, sfe_pyr** out);
+void sfe_pyr_destroy(sfe_pyr* pyr);
+int sfe_pyr_level_size(const sfe_pyr* pyr, int level, int* w, int* h, int* pitch_floats);
+/* Algorithmic HBM bytes of building ONE frame: 3*w*h read + 4*sum(level pixels)*planes written. */
+int64_t sfe_pyr_bytes_per_frame(const sfe_pyr* pyr);
+
+/* Replaces MakePyramid(img, depth) (matcher.cpp:317 -> hessian.h:95-126 / klt.h:98-137 /
+ * brute.h:59-80) for `count` frames starting at slot `first`.  bgr: 8-bit interleaved
+ * 3-channel rows (the CV_8UC3 frames of video.cpp:185), row_stride / frame_stride in bytes. */
+int sfe_pyr_build(sfe_ctx* ctx, sfe_pyr* pyr, const uint8_t* bgr_host, size_t row_stride,
+                  size_t frame_stride, int first, int count);
+int sfe_pyr_build_dev(sfe_ctx* ctx, sfe_pyr* pyr, const uint8_t* bgr_dev, size_t row_stride,
+                      size_t frame_stride, int first, int count);
+/* Copies one level plane (0 image, 1 gradx, 2 grady) of one frame to a dense w*h host array. */
+int sfe_pyr_download(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int plane,
+                     float* host_dst);
+
+/* ---- P1: forward/backward patch tracking (the live path) ------------------------------ */
+
+/* Replaces the free function TrackFeature (matcher.cpp:173-206) -- GetPatches + TrackFeature
+ * forward, GetPatches + TrackFeature backward, status and 0.3 px consistency gate -- for a
+ * batch of features, i.e. the body of the FindMatches loop (matcher.cpp:218-270) minus the
+ * host-side map bookkeeping.
+ *
+ * Feature i belongs to pair p = i / n_per_pair and is tracked from frame (from_first + p) of
+ * `from` to frame (to_first + p) of `to` (the same pyramid object may be passed twice).
+ *   from_xy  [n][2]  in   template position in the `from` frame           (from_pt)
+ *   to_xy    [n][2]  in   initial guess; out: tracked position, unchanged when the forward
+ *                         track fails (hessian.h:262 semantics)             (to_pt)
+ *   levels   [n] or NULL  pyramid levels to use per feature (3 or 6, matcher.cpp:227-229);
+ *                         NULL = default_levels for all
+ *   thr, maxit, fb_max    0.001, 10, 0.3 in the reference (matcher.cpp:176,182,201)
+ *   back_xy  [n][2]  out  backward-tracked position                       (back_pt)
+ *   status_fwd/status_bwd [n] out  sfe_status of each direction           (s1, s2)
+ *   accepted [n]     out  1 iff both OK and |from - back| <= fb_max       (return value)
+ *   steps    [n] or NULL out  Newton steps spent on the feature (forward + backward)
+ */
+int sfe_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                 int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                 const int32_t* levels, int default_levels, float thr, int maxit, float fb_max,
+                 float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted,
+                 int32_t* steps);
+int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                     int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                     const int32_t* levels, int default_levels, float thr, int maxit,
+                     float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                     uint8_t* accepted, int32_t* steps);
+
+/* Debug/parity accessors, one call per feature list on frame `frame` of `pyr`:
+ * GetPatch (hessian.h:54-93): patches [n][169], mean [n], sumsq [n]. */
+int sfe_get_patches(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int n,
+                    const float* xy, float* patches, float* mean, float* sumsq);
+/* BruteHessian (hessian.h:147-172) of template (tmpl pyr/frame at tmpl_xy) against
+ * (search pyr/frame at xy) on `level`: out [n][7] = sad0, dx, dy, dxx, dxy, dyx, dyy. */
+int sfe_brute_hessian(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const sfe_pyr* search,
+                      int search_frame, int level, int n, const float* tmpl_xy, const float* xy,
+                      float* out7);
+
+/* ---- P2: KLTTracker (klt.h) ------------------------------------------------------------ */
+
+/* klt.h:258-424 forward/backward with the same gate as above; all levels of the pyramid are
+ * used (klt.h:409) and the coarse-level threshold is 50x (klt.h:413). */
+int sfe_klt_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                     int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                     int32_t* status_bwd, uint8_t* accepted, int32_t* steps);
+int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                         int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                         float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                         int32_t* status_bwd, uint8_t* accepted, int32_t* steps);
+/* The symmetric-KLT normal equations of klt.h:286-353 at one point per feature:
+ * out [n][24] = A(4) B(4) C(4) RS(2) VW(2) U(4) e(2) d(2), row-major 2x2 blocks. */
+int sfe_klt_system(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const sfe_pyr* search,
+                   int search_frame, int level, int n, const float* tmpl_xy, const float* xy,
+                   float* out24);
+
+/* ---- P3: BruteTracker dense SSD window search (brute.h) -------------------------------- */
+
+/* brute.h:129-164 with the search schedule passed explicitly as {window,res} pairs
+ * (brute.h:147-148 for coarse levels, :154-158 for level 0).  best_sad [n], positions
+ * (total window positions evaluated) may be NULL. */
+int sfe_brute_track(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                    int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                    const float* coarse_sched, int n_coarse, const float* fine_sched, int n_fine,
+                    int32_t* status, float* best_sad, int64_t* positions);
+int sfe_brute_track_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
+                        int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
+                        const float* coarse_sched, int n_coarse, const float* fine_sched,
+                        int n_fine, int32_t* status, float* best_sad);
+
+/* ---- P4: 256-bit Hamming top-2 + ratio test -------------------------------------------- */
+
+/* The descriptor matcher BASELINE.json asks for (no counterpart in the reference; specified
+ * against cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2)).  q [nq][8] u32, t [nt][8] u32.
+ * idx/dist [nq][2]: best and second-best train row and distance, lowest index wins ties;
+ * missing neighbours are -1 / 257.  pass [nq] (may be NULL) = d1 <= max_dist and
+ * d1*ratio_den < d2*ratio_num.  `batch` independent (q,t) problems are laid out back to back
+ * (q: batch*nq rows, t: batch*nt rows). */
+int sfe_match_hamming256(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt,
+                         int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
+                         int32_t* dist, uint8_t* pass);
+int sfe_match_hamming256_dev(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt,
+                             int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
+                             int32_t* dist, uint8_t* pass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMFE_H_ */

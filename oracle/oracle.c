@@ -278,6 +278,25 @@ orc_pyr* orc_pyr_build(const uint8_t* bgr, int w, int h, size_t stride, int dept
   return p;
 }
 
+/* Wrap caller-provided planes (dense, row pitch == w) as a pyramid: lets tests run the trackers on
+ * planes produced by the real OpenCV.  planes[level*3 + {0,1,2}] = img, gx, gy (gx/gy may be NULL). */
+orc_pyr* orc_pyr_from_planes(int depth, int flavor, const int* ws, const int* hs, const float* const* planes) {
+  if (depth < 1 || depth > ORC_MAX_LEVELS) return NULL;
+  orc_pyr* p = (orc_pyr*)calloc(1, sizeof(orc_pyr));
+  p->depth = depth;
+  p->flavor = flavor;
+  for (int i = 0; i < depth; ++i) {
+    orc_plane* dst[3] = {&p->img[i], &p->gx[i], &p->gy[i]};
+    for (int k = 0; k < 3; ++k) {
+      const float* src = planes[i * 3 + k];
+      if (!src) continue;
+      plane_alloc(dst[k], ws[i], hs[i]);
+      memcpy(dst[k]->data, src, sizeof(float) * (size_t)ws[i] * hs[i]);
+    }
+  }
+  return p;
+}
+
 void orc_pyr_free(orc_pyr* p) {
   if (!p) return;
   for (int i = 0; i < ORC_MAX_LEVELS; ++i) {
@@ -783,7 +802,10 @@ int orc_brute_track_feature(const orc_pyr* tmpl_pyr, float tx, float ty, const o
     for (int k = 0; k < n_coarse; ++k)
       sad = orc_brute_search_best(search, i, patches[i], pm[i], pq[i], coarse_sched[2 * k],
                                   coarse_sched[2 * k + 1], &px, &py, npos);
-    if (sad > 100) return ORC_OUT_OF_BOUNDS;    /* :149 */
+    if (sad > 100) {                            /* :149 */
+      if (best_sad) *best_sad = sad;
+      return ORC_OUT_OF_BOUNDS;
+    }
     px *= 2.f; py *= 2.f;
   }
   for (int k = 0; k < n_fine; ++k)

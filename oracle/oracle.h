@@ -84,6 +84,8 @@ void orc_rect_subpix(const float* img, int w, int h, int n, int m, float cx, flo
 
 /* ---- pyramids ------------------------------------------------------------ */
 orc_pyr* orc_pyr_build(const uint8_t* bgr, int w, int h, size_t stride, int depth, int flavor);
+orc_pyr* orc_pyr_from_planes(int depth, int flavor, const int* ws, const int* hs,
+                             const float* const* planes /* [depth*3]: img,gx,gy */);
 void orc_pyr_free(orc_pyr* p);
 int orc_pyr_depth(const orc_pyr* p);
 int orc_pyr_w(const orc_pyr* p, int level);

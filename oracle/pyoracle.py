@@ -57,6 +57,8 @@ def lib(fast=False, native=False):
     L.orc_rect_subpix.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int]
     L.orc_pyr_build.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int]
     L.orc_pyr_build.restype = vp
+    L.orc_pyr_from_planes.argtypes = [C.c_int, C.c_int, i32p, i32p, C.POINTER(f32p)]
+    L.orc_pyr_from_planes.restype = vp
     L.orc_pyr_free.argtypes = [vp]
     for fn in (L.orc_pyr_depth,):
         fn.argtypes = [vp]
@@ -163,6 +165,29 @@ class Pyramid:
             raise ValueError("orc_pyr_build failed")
         self.depth = depth
         self.flavor = flavor
+
+    @classmethod
+    def from_planes(cls, planes, flavor=FLAVOR_HESSIAN, fast=False):
+        """planes: list over levels of a 2-D array (image only) or a tuple (img, gx, gy)."""
+        self = cls.__new__(cls)
+        self._L = lib(fast=fast)
+        depth = len(planes)
+        ws = (C.c_int32 * depth)()
+        hs = (C.c_int32 * depth)()
+        ptrs = (C.POINTER(C.c_float) * (3 * depth))()
+        keep = []
+        for i, lvl in enumerate(planes):
+            trio = lvl if isinstance(lvl, (tuple, list)) else (lvl, None, None)
+            hs[i], ws[i] = trio[0].shape
+            for k, a in enumerate(trio):
+                if a is None:
+                    continue
+                a = _f32(a)
+                keep.append(a)
+                ptrs[3 * i + k] = _p(a, C.c_float)
+        self.h = self._L.orc_pyr_from_planes(depth, flavor, ws, hs, ptrs)
+        self.depth, self.flavor = depth, flavor
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -1,0 +1,577 @@
+// capi.cu -- the C ABI of libslamfe.so (include/slamfe.h): contexts, pyramid handles, and the
+// host-pointer / device-pointer entry points.  No CPU fallback anywhere: every entry point
+// either runs the CUDA path or reports SFE_ERR_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "sfe_common.cuh"
+
+struct sfe_ctx {
+  int device;
+  cudaStream_t own_stream;
+  cudaStream_t stream;
+  float* d_mask;
+  float h_mask[SFE_PLEN];
+  // grow-on-demand device scratch for the host-pointer entry points
+  void* scratch;
+  size_t scratch_cap;
+  void* ham_ws;
+  size_t ham_cap;
+  int64_t launches;
+  char err[512];
+};
+
+struct sfe_pyr {
+  sfe_ctx* ctx;
+  int flavor;
+  int planes;
+  PyrView view;
+  float* storage;
+  size_t storage_floats;
+  int64_t bytes_per_frame;
+};
+
+namespace {
+
+int fail(sfe_ctx* c, int code, const char* fmt, const char* detail) {
+  if (c) snprintf(c->err, sizeof(c->err), fmt, detail);
+  return code;
+}
+
+#define CU(call)                                                                     \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) return fail(ctx, SFE_ERR_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+int use_device(sfe_ctx* ctx) {
+  CU(cudaSetDevice(ctx->device));
+  return SFE_SUCCESS;
+}
+
+int launched(sfe_ctx* ctx, int r, const char* what) {
+  if (r < 0) return fail(ctx, SFE_ERR_CUDA, what, cudaGetErrorString((cudaError_t)(-r)));
+  ctx->launches += r;
+  return SFE_SUCCESS;
+}
+
+// hessian.h:11-30 (same arithmetic as oracle.c orc_mask13)
+void build_mask(float* mask) {
+  const int n = SFE_PATCH;
+  for (int y = 0; y < n; ++y)
+    for (int x = 0; x < n; ++x) {
+      double rx = 0.5 * n - x, ry = 0.5 * n - y;
+      mask[y * n + x] = (float)(1. / (15. + (rx * rx + ry * ry)));
+    }
+  double sum = 0;
+  for (int i = 0; i < SFE_PLEN; ++i) sum += mask[i];
+  double scale = SFE_PLEN / sum;
+  for (int i = 0; i < SFE_PLEN; ++i) mask[i] = (float)(mask[i] * scale);
+}
+
+int ensure_scratch(sfe_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_cap) return SFE_SUCCESS;
+  if (ctx->scratch) CU(cudaFree(ctx->scratch));
+  ctx->scratch = nullptr;
+  ctx->scratch_cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMalloc(&ctx->scratch, cap);
+  if (e != cudaSuccess) return fail(ctx, SFE_ERR_NOMEM, "cudaMalloc(scratch): %s", cudaGetErrorString(e));
+  ctx->scratch_cap = cap;
+  return SFE_SUCCESS;
+}
+
+// bump allocator over the scratch buffer (256-byte aligned pieces)
+struct Carver {
+  char* base;
+  size_t off;
+  template <class T>
+  T* take(size_t count) {
+    T* p = (T*)(base + off);
+    off += (count * sizeof(T) + 255) & ~(size_t)255;
+    return p;
+  }
+};
+size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+int check_pairs(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                int n_per_pair) {
+  if (!from || !to || n < 0 || n_per_pair <= 0) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (n == 0) return SFE_SUCCESS;
+  int npairs = (n + n_per_pair - 1) / n_per_pair;
+  if (from_first < 0 || to_first < 0 || from_first + npairs > from->view.batch || to_first + npairs > to->view.batch)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "frame pair range exceeds the pyramid batch");
+  if (from->view.w[0] != to->view.w[0] || from->view.h[0] != to->view.h[0])
+    return fail(ctx, SFE_ERR_INVALID, "%s", "from/to pyramids differ in frame size");
+  return SFE_SUCCESS;
+}
+
+}  // namespace
+
+namespace {
+// shared host-pointer wrapper of the two forward/backward trackers
+template <class Launch>
+int track_host(sfe_ctx* ctx, int n, const float* from_xy, float* to_xy, const int32_t* levels, float* back_xy,
+               int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps, Launch launch) {
+  size_t need = padded(8 * (size_t)n) * 3 + padded(4 * (size_t)n) * 4 + padded(n);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  float* d_from = c.take<float>(2 * (size_t)n);
+  float* d_to = c.take<float>(2 * (size_t)n);
+  float* d_back = c.take<float>(2 * (size_t)n);
+  int32_t* d_lv = c.take<int32_t>(n);
+  int32_t* d_s1 = c.take<int32_t>(n);
+  int32_t* d_s2 = c.take<int32_t>(n);
+  int32_t* d_steps = c.take<int32_t>(n);
+  uint8_t* d_acc = c.take<uint8_t>(n);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_from, from_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_to, to_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  if (levels) CU(cudaMemcpyAsync(d_lv, levels, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = launch(d_from, d_to, levels ? d_lv : nullptr, d_back, d_s1, d_s2, d_acc, d_steps);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(to_xy, d_to, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (back_xy) CU(cudaMemcpyAsync(back_xy, d_back, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (status_fwd) CU(cudaMemcpyAsync(status_fwd, d_s1, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (status_bwd) CU(cudaMemcpyAsync(status_bwd, d_s2, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (accepted) CU(cudaMemcpyAsync(accepted, d_acc, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (steps) CU(cudaMemcpyAsync(steps, d_steps, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+}  // namespace
+
+namespace {
+template <class Launch>
+int point_pair_host(sfe_ctx* ctx, int n, const float* txy, const float* xy, float* out, int out_per, Launch launch) {
+  size_t need = 2 * padded(8 * (size_t)n) + padded(4 * (size_t)n * out_per);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  float* d_t = c.take<float>(2 * (size_t)n);
+  float* d_x = c.take<float>(2 * (size_t)n);
+  float* d_o = c.take<float>((size_t)n * out_per);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_t, txy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_x, xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = launched(ctx, launch(d_t, d_x, d_o, s), "launch: %s");
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, d_o, 4 * (size_t)n * out_per, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+bool frame_ok(const sfe_pyr* p, int frame, int level) {
+  return p && frame >= 0 && frame < p->view.batch && level >= 0 && level < p->view.depth;
+}
+}  // namespace
+
+extern "C" {
+
+int sfe_create(int device, sfe_ctx** out) {
+  if (!out) return SFE_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SFE_ERR_CUDA;
+  sfe_ctx* ctx = new (std::nothrow) sfe_ctx();
+  if (!ctx) return SFE_ERR_NOMEM;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return SFE_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  build_mask(ctx->h_mask);
+  if (cudaMalloc(&ctx->d_mask, sizeof(ctx->h_mask)) != cudaSuccess ||
+      cudaMemcpy(ctx->d_mask, ctx->h_mask, sizeof(ctx->h_mask), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SFE_ERR_CUDA;
+  }
+  *out = ctx;
+  return SFE_SUCCESS;
+}
+
+void sfe_destroy(sfe_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->ham_ws) cudaFree(ctx->ham_ws);
+  cudaFree(ctx->d_mask);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* sfe_last_error(const sfe_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int sfe_set_stream(sfe_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return SFE_ERR_INVALID;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return SFE_SUCCESS;
+}
+
+int sfe_sync(sfe_ctx* ctx) {
+  if (!ctx) return SFE_ERR_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SFE_SUCCESS;
+}
+
+int sfe_get_mask(sfe_ctx* ctx, float* mask169) {
+  if (!ctx || !mask169) return SFE_ERR_INVALID;
+  CU(cudaMemcpy(mask169, ctx->d_mask, sizeof(float) * SFE_PLEN, cudaMemcpyDeviceToHost));
+  return SFE_SUCCESS;
+}
+
+int sfe_host_alloc(sfe_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return SFE_ERR_INVALID;
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return SFE_SUCCESS;
+}
+
+int sfe_host_free(sfe_ctx* ctx, void* p) {
+  if (!ctx) return SFE_ERR_INVALID;
+  CU(cudaFreeHost(p));
+  return SFE_SUCCESS;
+}
+
+int64_t sfe_launch_count(const sfe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---- pyramids ---------------------------------------------------------------------------- */
+
+int sfe_pyr_create(sfe_ctx* ctx, int w, int h, int depth, int flavor, int batch, sfe_pyr** out) {
+  if (!ctx || !out) return SFE_ERR_INVALID;
+  *out = nullptr;
+  if (w < 1 || h < 1 || depth < 1 || depth > SFE_MAX_LEVELS || batch < 1 || flavor < SFE_HESSIAN || flavor > SFE_BRUTE)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad pyramid geometry");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  sfe_pyr* p = new (std::nothrow) sfe_pyr();
+  if (!p) return SFE_ERR_NOMEM;
+  memset(p, 0, sizeof(*p));
+  p->ctx = ctx;
+  p->flavor = flavor;
+  p->planes = flavor == SFE_KLT ? 3 : 1;
+  PyrView& v = p->view;
+  v.depth = depth;
+  v.batch = batch;
+  size_t total = 0;
+  int64_t px = 0;
+  int lw = w, lh = h;
+  for (int l = 0; l < depth; ++l) {
+    v.w[l] = lw;
+    v.h[l] = lh;
+    v.pitch[l] = (lw + 3) & ~3;
+    // frame stride rounded to 32 floats so every frame plane starts 128-byte aligned
+    v.frame_stride[l] = ((long long)v.pitch[l] * lh + 31) & ~31LL;
+    total += (size_t)v.frame_stride[l] * batch * p->planes;
+    px += (int64_t)lw * lh;
+    lw = (lw + 1) / 2;  // hessian.h:108
+    lh = (lh + 1) / 2;
+  }
+  p->bytes_per_frame = 3LL * w * h + 4LL * px * p->planes;
+  cudaError_t e = cudaMalloc(&p->storage, total * sizeof(float));
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(ctx, SFE_ERR_NOMEM, "cudaMalloc(pyramid): %s", cudaGetErrorString(e));
+  }
+  p->storage_floats = total;
+  size_t off = 0;
+  for (int pl = 0; pl < p->planes; ++pl)
+    for (int l = 0; l < depth; ++l) {
+      v.base[pl][l] = p->storage + off;
+      off += (size_t)v.frame_stride[l] * batch;
+    }
+  *out = p;
+  return SFE_SUCCESS;
+}
+
+void sfe_pyr_destroy(sfe_pyr* pyr) {
+  if (!pyr) return;
+  cudaSetDevice(pyr->ctx->device);
+  cudaStreamSynchronize(pyr->ctx->stream);
+  cudaFree(pyr->storage);
+  delete pyr;
+}
+
+int sfe_pyr_level_size(const sfe_pyr* pyr, int level, int* w, int* h, int* pitch_floats) {
+  if (!pyr || level < 0 || level >= pyr->view.depth) return SFE_ERR_INVALID;
+  if (w) *w = pyr->view.w[level];
+  if (h) *h = pyr->view.h[level];
+  if (pitch_floats) *pitch_floats = pyr->view.pitch[level];
+  return SFE_SUCCESS;
+}
+
+int64_t sfe_pyr_bytes_per_frame(const sfe_pyr* pyr) { return pyr ? pyr->bytes_per_frame : 0; }
+
+int sfe_pyr_build_dev(sfe_ctx* ctx, sfe_pyr* pyr, const uint8_t* bgr_dev, size_t row_stride, size_t frame_stride,
+                      int first, int count) {
+  if (!ctx || !pyr || !bgr_dev) return SFE_ERR_INVALID;
+  if (count == 0) return SFE_SUCCESS;
+  if (first < 0 || count < 0 || first + count > pyr->view.batch || row_stride < (size_t)3 * pyr->view.w[0])
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad frame range or stride");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return launched(ctx, launch_pyr_build(pyr->view, pyr->flavor, bgr_dev, row_stride, frame_stride, first, count, ctx->stream),
+                  "pyramid launch: %s");
+}
+
+int sfe_pyr_build(sfe_ctx* ctx, sfe_pyr* pyr, const uint8_t* bgr_host, size_t row_stride, size_t frame_stride,
+                  int first, int count) {
+  if (!ctx || !pyr || !bgr_host) return SFE_ERR_INVALID;
+  if (count == 0) return SFE_SUCCESS;
+  if (first < 0 || count < 0 || first + count > pyr->view.batch || row_stride < (size_t)3 * pyr->view.w[0])
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad frame range or stride");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  const int w = pyr->view.w[0], h = pyr->view.h[0];
+  const size_t dense_row = (size_t)3 * w, dense_frame = dense_row * h;
+  int rc = ensure_scratch(ctx, dense_frame * count);
+  if (rc) return rc;
+  uint8_t* d = (uint8_t*)ctx->scratch;
+  if (row_stride == dense_row && (frame_stride == dense_frame || count == 1)) {
+    CU(cudaMemcpyAsync(d, bgr_host, dense_frame * count, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int f = 0; f < count; ++f)
+      CU(cudaMemcpy2DAsync(d + f * dense_frame, dense_row, bgr_host + f * frame_stride, row_stride, dense_row, h,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = launched(ctx, launch_pyr_build(pyr->view, pyr->flavor, d, dense_row, dense_frame, first, count, ctx->stream),
+                "pyramid launch: %s");
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SFE_SUCCESS;
+}
+
+int sfe_pyr_download(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int plane, float* host_dst) {
+  if (!ctx || !pyr || !host_dst || frame < 0 || frame >= pyr->view.batch || level < 0 || level >= pyr->view.depth ||
+      plane < 0 || plane >= pyr->planes)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad download arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  ImgView im = img_of(pyr->view, plane, level, frame);
+  CU(cudaMemcpy2DAsync(host_dst, sizeof(float) * im.w, im.p, sizeof(float) * im.pitch, sizeof(float) * im.w, im.h,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SFE_SUCCESS;
+}
+
+/* ---- P1 ---------------------------------------------------------------------------------- */
+
+int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                     int n_per_pair, const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                     uint8_t* accepted, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
+  if (rc || n == 0) return rc;
+  if (!from_xy || !to_xy || default_levels < 1 || maxit < 0) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (from->flavor != SFE_HESSIAN || to->flavor != SFE_HESSIAN)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_track_fb needs SFE_HESSIAN pyramids");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, levels, default_levels, thr, maxit, fb_max,
+              back_xy, status_fwd, status_bwd, accepted, steps};
+  return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, ctx->stream), "track launch: %s");
+}
+
+
+int sfe_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                 int n_per_pair, const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                 float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                 uint8_t* accepted, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (n == 0) return SFE_SUCCESS;
+  if (n < 0 || !from_xy || !to_xy) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return track_host(ctx, n, from_xy, to_xy, levels, back_xy, status_fwd, status_bwd, accepted, steps,
+                    [&](float* df, float* dt, int32_t* dl, float* db, int32_t* s1, int32_t* s2, uint8_t* acc, int32_t* st) {
+                      return sfe_track_fb_dev(ctx, from, from_first, to, to_first, n, n_per_pair, df, dt, dl,
+                                              default_levels, thr, maxit, fb_max, db, s1, s2, acc, st);
+                    });
+}
+
+int sfe_get_patches(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int n, const float* xy, float* patches,
+                    float* mean, float* sumsq) {
+  if (!ctx || !pyr || n < 0 || !xy || !patches || !mean || !sumsq || frame < 0 || frame >= pyr->view.batch || level < 0 ||
+      level >= pyr->view.depth)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad get_patches arguments");
+  if (n == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  size_t need = padded(8 * (size_t)n) + padded(4 * (size_t)n * SFE_PLEN) + 2 * padded(4 * (size_t)n);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  float* d_xy = c.take<float>(2 * (size_t)n);
+  float* d_p = c.take<float>((size_t)n * SFE_PLEN);
+  float* d_m = c.take<float>(n);
+  float* d_q = c.take<float>(n);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_xy, xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = launched(ctx, launch_get_patches(pyr->view, frame, level, n, d_xy, d_p, d_m, d_q, s), "get_patches launch: %s");
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(patches, d_p, 4 * (size_t)n * SFE_PLEN, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(mean, d_m, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(sumsq, d_q, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+
+
+int sfe_brute_hessian(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const sfe_pyr* search, int search_frame,
+                      int level, int n, const float* tmpl_xy, const float* xy, float* out7) {
+  if (!ctx || n < 0 || !tmpl_xy || !xy || !out7 || !frame_ok(tmpl, tmpl_frame, level) || !frame_ok(search, search_frame, level))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad brute_hessian arguments");
+  if (n == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return point_pair_host(ctx, n, tmpl_xy, xy, out7, 7, [&](float* dt, float* dx, float* dout, cudaStream_t s) {
+    return launch_brute_hessian(tmpl->view, tmpl_frame, search->view, search_frame, level, n, dt, dx, dout, ctx->d_mask, s);
+  });
+}
+
+/* ---- P2 ---------------------------------------------------------------------------------- */
+
+int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                         int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, float fb_max,
+                         float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
+  if (rc || n == 0) return rc;
+  if (!from_xy || !to_xy || maxit < 0) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (from->flavor != SFE_KLT || to->flavor != SFE_KLT)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_klt_track_fb needs SFE_KLT pyramids");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, nullptr, from->view.depth, thr, maxit, fb_max,
+              back_xy, status_fwd, status_bwd, accepted, steps};
+  return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, ctx->stream), "klt launch: %s");
+}
+
+int sfe_klt_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                     int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, float fb_max,
+                     float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (n == 0) return SFE_SUCCESS;
+  if (n < 0 || !from_xy || !to_xy) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return track_host(ctx, n, from_xy, to_xy, nullptr, back_xy, status_fwd, status_bwd, accepted, steps,
+                    [&](float* df, float* dt, int32_t*, float* db, int32_t* s1, int32_t* s2, uint8_t* acc, int32_t* st) {
+                      return sfe_klt_track_fb_dev(ctx, from, from_first, to, to_first, n, n_per_pair, df, dt, thr, maxit,
+                                                  fb_max, db, s1, s2, acc, st);
+                    });
+}
+
+int sfe_klt_system(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const sfe_pyr* search, int search_frame, int level,
+                   int n, const float* tmpl_xy, const float* xy, float* out24) {
+  if (!ctx || n < 0 || !tmpl_xy || !xy || !out24 || !frame_ok(tmpl, tmpl_frame, level) || !frame_ok(search, search_frame, level))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad klt_system arguments");
+  if (tmpl->flavor != SFE_KLT || search->flavor != SFE_KLT)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_klt_system needs SFE_KLT pyramids");
+  if (n == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return point_pair_host(ctx, n, tmpl_xy, xy, out24, 24, [&](float* dt, float* dx, float* dout, cudaStream_t s) {
+    return launch_klt_system(tmpl->view, tmpl_frame, search->view, search_frame, level, n, dt, dx, dout, ctx->d_mask, s);
+  });
+}
+
+/* ---- P3 ---------------------------------------------------------------------------------- */
+
+int sfe_brute_track_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                        int n_per_pair, const float* from_xy, float* to_xy, const float* coarse_sched, int n_coarse,
+                        const float* fine_sched, int n_fine, int32_t* status, float* best_sad) {
+  if (!ctx) return SFE_ERR_INVALID;
+  int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
+  if (rc || n == 0) return rc;
+  if (!from_xy || !to_xy || n_coarse < 0 || n_fine < 0 || n_coarse > 8 || n_fine > 8 || (n_coarse && !coarse_sched) ||
+      (n_fine && !fine_sched))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad brute_track arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  // schedules are host arrays even in the _dev variant (they are tiny call parameters)
+  return launched(ctx,
+                  launch_brute_track(from->view, to->view, from_first, to_first, n, n_per_pair, from_xy, to_xy, coarse_sched,
+                                     n_coarse, fine_sched, n_fine, status, best_sad, nullptr, ctx->stream),
+                  "brute_track launch: %s");
+}
+
+int sfe_brute_track(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
+                    int n_per_pair, const float* from_xy, float* to_xy, const float* coarse_sched, int n_coarse,
+                    const float* fine_sched, int n_fine, int32_t* status, float* best_sad, int64_t* positions) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (n == 0) return SFE_SUCCESS;
+  int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
+  if (rc) return rc;
+  if (!from_xy || !to_xy || n_coarse < 0 || n_fine < 0 || n_coarse > 8 || n_fine > 8 || (n_coarse && !coarse_sched) ||
+      (n_fine && !fine_sched))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad brute_track arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  size_t need = 2 * padded(8 * (size_t)n) + 2 * padded(4 * (size_t)n) + 256;
+  rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  float* d_from = c.take<float>(2 * (size_t)n);
+  float* d_to = c.take<float>(2 * (size_t)n);
+  int32_t* d_st = c.take<int32_t>(n);
+  float* d_sad = c.take<float>(n);
+  unsigned long long* d_pos = c.take<unsigned long long>(1);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_from, from_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_to, to_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_pos, 0, sizeof(unsigned long long), s));
+  rc = launched(ctx,
+                launch_brute_track(from->view, to->view, from_first, to_first, n, n_per_pair, d_from, d_to, coarse_sched,
+                                   n_coarse, fine_sched, n_fine, d_st, d_sad, d_pos, s),
+                "brute_track launch: %s");
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(to_xy, d_to, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (status) CU(cudaMemcpyAsync(status, d_st, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (best_sad) CU(cudaMemcpyAsync(best_sad, d_sad, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  unsigned long long pos = 0;
+  CU(cudaMemcpyAsync(&pos, d_pos, sizeof(pos), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (positions) *positions = (int64_t)pos;
+  return SFE_SUCCESS;
+}
+
+/* ---- P4 ---------------------------------------------------------------------------------- */
+
+int sfe_match_hamming256_dev(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int batch,
+                             int ratio_num, int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass) {
+  if (!ctx || nq < 0 || nt < 0 || batch < 1 || !idx || !dist || (nq && !q) || (nt && !t))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad hamming arguments");
+  if (nt > (1 << 22)) return fail(ctx, SFE_ERR_INVALID, "%s", "nt exceeds 4M train descriptors per call");
+  if (nq == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return launched(ctx,
+                  launch_hamming256(q, nq, t, nt, batch, ratio_num, ratio_den, max_dist, idx, dist, pass, &ctx->ham_ws,
+                                    &ctx->ham_cap, ctx->stream),
+                  "hamming launch: %s");
+}
+
+int sfe_match_hamming256(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int ratio_num,
+                         int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass) {
+  if (!ctx || nq < 0 || nt < 0 || batch < 1 || !idx || !dist || (nq && !q) || (nt && !t))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad hamming arguments");
+  if (nq == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  const size_t qb = 32 * (size_t)nq * batch, tb = 32 * (size_t)nt * batch, ob = 8 * (size_t)nq * batch;
+  size_t need = padded(qb) + padded(tb) + 2 * padded(ob) + padded((size_t)nq * batch);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  uint32_t* d_q = c.take<uint32_t>(8 * (size_t)nq * batch);
+  uint32_t* d_t = c.take<uint32_t>(8 * (size_t)nt * batch);
+  int32_t* d_i = c.take<int32_t>(2 * (size_t)nq * batch);
+  int32_t* d_d = c.take<int32_t>(2 * (size_t)nq * batch);
+  uint8_t* d_p = c.take<uint8_t>((size_t)nq * batch);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_q, q, qb, cudaMemcpyHostToDevice, s));
+  if (nt) CU(cudaMemcpyAsync(d_t, t, tb, cudaMemcpyHostToDevice, s));
+  rc = sfe_match_hamming256_dev(ctx, d_q, nq, d_t, nt, batch, ratio_num, ratio_den, max_dist, d_i, d_d, pass ? d_p : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(idx, d_i, ob, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(dist, d_d, ob, cudaMemcpyDeviceToHost, s));
+  if (pass) CU(cudaMemcpyAsync(pass, d_p, (size_t)nq * batch, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// hamming.cu -- brute-force 256-bit Hamming matcher with fused top-2 and ratio test (P4).
+//
+// There is no descriptor matcher in the reference; the behaviour is specified
+// against cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2): distance = popcount(xor), best and second
+// best train rows per query, LOWEST train index wins ties (oracle.c orc_hamming256_top2).
+//
+// Integer-ALU work, not a GEMM: each thread keeps QPT query descriptors in registers (8 words
+// each), train descriptors stream through shared memory in tiles and are read as warp-wide
+// broadcasts (2 x LDS.128 per descriptor), the distance is 8 x (LOP3 xor + POPC) and the running
+// top-2 is three min/max on packed keys  key = dist << 22 | train_index  -- ordering by key IS the
+// tie rule, independent of the order tiles are visited, so the train set can be split over CTAs.
+// A finalize kernel merges the per-split keys, decodes them and applies the integer ratio test
+// d1 * den < d2 * num.
+#include "sfe_common.cuh"
+
+namespace {
+
+constexpr int HM_THREADS = 128;
+constexpr int HM_QPT = 2;                    // queries per thread
+constexpr int HM_QPB = HM_THREADS * HM_QPT;  // queries per CTA
+constexpr int HM_TT = 256;                   // train descriptors per shared-memory tile
+constexpr uint32_t KEY_NONE = 0xffffffffu;
+constexpr int IDX_BITS = 22;                 // nt <= 4M per call
+
+__device__ __forceinline__ void top2_update(uint32_t key, uint32_t& k1, uint32_t& k2) {
+  uint32_t hi = max(k1, key);
+  k1 = min(k1, key);
+  k2 = min(k2, hi);
+}
+
+__global__ void __launch_bounds__(HM_THREADS) hamming_kernel(const uint4* __restrict__ q, int nq,
+                                                             const uint4* __restrict__ t, int nt, int splits,
+                                                             uint2* __restrict__ keys /* [batch][splits][nq] */) {
+  __shared__ uint4 tile[HM_TT * 2];
+  const int b = blockIdx.z, split = blockIdx.y;
+  const uint4* qb = q + (size_t)b * nq * 2;
+  const uint4* tb = t + (size_t)b * nt * 2;
+  const int per = (nt + splits - 1) / splits;
+  const int t0 = split * per, t1 = min(nt, t0 + per);
+
+  uint4 qa[HM_QPT], qc[HM_QPT];
+  uint32_t k1[HM_QPT], k2[HM_QPT];
+  int qi[HM_QPT];
+#pragma unroll
+  for (int u = 0; u < HM_QPT; ++u) {
+    qi[u] = blockIdx.x * HM_QPB + u * HM_THREADS + threadIdx.x;
+    int qq = min(qi[u], nq - 1);
+    qa[u] = __ldg(qb + 2 * (size_t)qq);
+    qc[u] = __ldg(qb + 2 * (size_t)qq + 1);
+    k1[u] = k2[u] = KEY_NONE;
+  }
+
+  for (int base = t0; base < t1; base += HM_TT) {
+    const int cnt = min(HM_TT, t1 - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * 2; e += HM_THREADS) tile[e] = __ldg(tb + 2 * (size_t)base + e);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const uint4 ta = tile[2 * j], tc = tile[2 * j + 1];
+      const uint32_t jj = (uint32_t)(base + j);
+#pragma unroll
+      for (int u = 0; u < HM_QPT; ++u) {
+        int d = __popc(qa[u].x ^ ta.x) + __popc(qa[u].y ^ ta.y) + __popc(qa[u].z ^ ta.z) + __popc(qa[u].w ^ ta.w) +
+                __popc(qc[u].x ^ tc.x) + __popc(qc[u].y ^ tc.y) + __popc(qc[u].z ^ tc.z) + __popc(qc[u].w ^ tc.w);
+        top2_update(((uint32_t)d << IDX_BITS) | jj, k1[u], k2[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < HM_QPT; ++u)
+    if (qi[u] < nq) keys[((size_t)b * splits + split) * nq + qi[u]] = make_uint2(k1[u], k2[u]);
+}
+
+__global__ void hamming_finalize_kernel(const uint2* __restrict__ keys, int nq, int splits, int total /*batch*nq*/,
+                                        int ratio_num, int ratio_den, int max_dist, int32_t* __restrict__ idx,
+                                        int32_t* __restrict__ dist, uint8_t* __restrict__ pass) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int b = g / nq, i = g - b * nq;
+  uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+  for (int s = 0; s < splits; ++s) {
+    uint2 k = keys[((size_t)b * splits + s) * nq + i];
+    top2_update(k.x, k1, k2);
+    top2_update(k.y, k1, k2);
+  }
+  int i1 = -1, i2 = -1, d1 = 257, d2 = 257;
+  if (k1 != KEY_NONE) { i1 = (int)(k1 & ((1u << IDX_BITS) - 1)); d1 = (int)(k1 >> IDX_BITS); }
+  if (k2 != KEY_NONE) { i2 = (int)(k2 & ((1u << IDX_BITS) - 1)); d2 = (int)(k2 >> IDX_BITS); }
+  idx[2 * (size_t)g] = i1; idx[2 * (size_t)g + 1] = i2;
+  dist[2 * (size_t)g] = d1; dist[2 * (size_t)g + 1] = d2;
+  if (pass) pass[g] = (uint8_t)(i1 >= 0 && d1 <= max_dist && (long long)d1 * ratio_den < (long long)d2 * ratio_num);
+}
+
+}  // namespace
+
+int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int ratio_num,
+                      int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass, void** ws, size_t* ws_cap, cudaStream_t s) {
+  if (nq <= 0 || batch <= 0) return 0;
+  if (nt > (1 << IDX_BITS)) return -(int)cudaErrorInvalidValue;
+  int qblocks = (nq + HM_QPB - 1) / HM_QPB;
+  // split the train set when the query tiles alone cannot fill the GPU (2 CTAs per SM target)
+  int splits = 1;
+  const int target = 148 * 4;
+  if (nt > 0 && qblocks * batch < target) splits = min((target + qblocks * batch - 1) / (qblocks * batch), (nt + HM_TT - 1) / HM_TT);
+  if (splits < 1) splits = 1;
+  // per-context key workspace [batch][splits][nq], grown on demand (calls are stream-ordered)
+  size_t need = (size_t)batch * splits * nq * sizeof(uint2);
+  if (need > *ws_cap) {
+    if (*ws) cudaFree(*ws);
+    cudaError_t e = cudaMalloc(ws, need);
+    if (e != cudaSuccess) { *ws = nullptr; *ws_cap = 0; return -(int)e; }
+    *ws_cap = need;
+  }
+  uint2* g_keys = (uint2*)*ws;
+  dim3 grid(qblocks, splits, batch);
+  hamming_kernel<<<grid, HM_THREADS, 0, s>>>((const uint4*)q, nq, (const uint4*)t, nt, splits, g_keys);
+  int total = batch * nq;
+  hamming_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(g_keys, nq, splits, total, ratio_num, ratio_den,
+                                                              max_dist, idx, dist, pass);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 2 : -(int)e;
+}

@@ -1,0 +1,65 @@
+// track_hessian.cu -- P1, the live path: HessianTracker forward/backward (track_impl.cuh,
+// MODE_HESSIAN) plus the GetPatch / BruteHessian parity accessors.
+#include "track_impl.cuh"
+
+namespace {
+
+// GetPatch (hessian.h:54-93) for n points of one level
+__global__ void get_patches_kernel(PyrView v, int frame, int level, int n, const float* __restrict__ xy,
+                                   float* __restrict__ patches, float* __restrict__ mean, float* __restrict__ sumsq) {
+  const int lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const LanePix lp = lane_pix(lane);
+  float T[SFE_SLOTS], m, q;
+  template_patch<MODE_HESSIAN>(img_of(v, 0, level, frame), xy[2 * i], xy[2 * i + 1], lp, T, m, q);
+#pragma unroll
+  for (int k = 0; k < SFE_SLOTS; ++k)
+    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = T[k];
+  if (lane == 0) { mean[i] = m; sumsq[i] = q; }
+}
+
+// BruteHessian (hessian.h:147-172) for n (template point, search point) pairs of one level
+__global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView tv, int tframe, PyrView sv, int sframe,
+                                                                       int level, int n, const float* __restrict__ txy,
+                                                                       const float* __restrict__ xy, float* __restrict__ out7,
+                                                                       const float* __restrict__ mask) {
+  __shared__ float tiles[TRK_WARPS][TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * TRK_WARPS + warp;
+  if (i >= n) return;
+  const LanePix lp = lane_pix(lane);
+  float mk[SFE_SLOTS];
+  load_mask(mask, lane, mk);
+  float T[SFE_SLOTS], m, q, d[6];
+  template_patch<MODE_HESSIAN>(img_of(tv, 0, level, tframe), txy[2 * i], txy[2 * i + 1], lp, T, m, q);
+  float s0 = brute_hessian<MODE_HESSIAN>(tiles[warp], img_of(sv, 0, level, sframe), T, m, q, mk, lp, xy[2 * i],
+                                         xy[2 * i + 1], lane, d);
+  if (lane == 0) {
+    out7[7 * i] = s0;
+    for (int k = 0; k < 6; ++k) out7[7 * i + 1 + k] = d[k];
+  }
+}
+
+}  // namespace
+
+int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask,
+                         cudaStream_t s) {
+  return launch_track_fb<MODE_HESSIAN>(from, to, a, mask, s);
+}
+
+int launch_get_patches(const PyrView& v, int frame, int level, int n, const float* xy, float* patches,
+                       float* mean, float* sumsq, cudaStream_t s) {
+  if (n <= 0) return 0;
+  get_patches_kernel<<<(n + 3) / 4, 128, 0, s>>>(v, frame, level, n, xy, patches, mean, sumsq);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
+}
+
+int launch_brute_hessian(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level, int n,
+                         const float* txy, const float* xy, float* out7, const float* mask, cudaStream_t s) {
+  if (n <= 0) return 0;
+  brute_hessian_kernel<<<(n + TRK_WARPS - 1) / TRK_WARPS, 32 * TRK_WARPS, 0, s>>>(tv, tframe, sv, sframe, level, n,
+                                                                                  txy, xy, out7, mask);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
+}

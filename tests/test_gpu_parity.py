@@ -1,0 +1,181 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libslamfe.so), against the
+CPU oracle on identical seeded inputs.  Bar: bit-exact for every output (float results are
+compared as bit patterns -- the GPU kernels and the oracle spell the same IEEE operations in the
+same order), identical status/accept flags.  north_star's own bar (1e-3 px, identical flags) is
+checked as well and is implied by the bit-exact one."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mask_matches_oracle(fe, po):
+    assert_bits_equal(fe.mask(), po.mask13(), "mask (hessian.h:11-30)")
+
+
+@pytest.mark.parametrize("shape,depth", [((480, 640), 6), ((97, 131), 5), ((270, 481), 8), ((33, 47), 3)])
+@pytest.mark.parametrize("flavor", [0, 1, 2])
+def test_pyramid_bit_exact(fe, po, synth, shape, depth, flavor):
+    H, W = shape
+    frames = synth.make_frames(7 + flavor, 2, H, W).numpy()
+    gp = fe.make_pyramid(frames, depth, flavor)
+    for f in range(2):
+        op = po.Pyramid(frames[f], depth, flavor)
+        for l in range(depth):
+            for plane in range(3 if flavor == 1 else 1):
+                assert_bits_equal(gp.plane(l, f, plane), op.plane(l, plane), "flavor %d frame %d level %d plane %d" % (flavor, f, l, plane))
+
+
+def _features(synth, n, H, W, seed=5, border=0.2):
+    return synth.make_features(seed, n, H, W, margin=16, border_frac=border)
+
+
+def test_get_patches_bit_exact(fe, po, pair640, synth):
+    A, _ = pair640
+    gp = fe.make_pyramid(A, 6)
+    op = po.Pyramid(A, 6)
+    rng = np.random.default_rng(3)
+    for level in range(6):
+        w, h = op.size(level)
+        n = 300
+        xy = np.stack([rng.uniform(0.02, w - 0.02, n), rng.uniform(0.02, h - 0.02, n)], 1).astype(np.float32)
+        # force the corners / edges, incl. the top-right region of OpenCV's getRectSubPix quirk
+        xy[:8] = [[0.5, 0.5], [w - 0.5, 0.5], [0.5, h - 0.5], [w - 0.5, h - 0.5], [w - 3.3, 0.2], [w - 6.9, 5.7], [6.4, 6.4], [6.6, 6.6]]
+        p, m, q = fe.get_patches(gp, level, xy)
+        for i in range(n):
+            d, mm, qq = po.hes_get_patch(op, level, xy[i, 0], xy[i, 1])
+            assert_bits_equal(p[i], d, "patch level %d #%d at %s" % (level, i, xy[i]))
+            assert_bits_equal(np.float32([m[i], q[i]]), np.float32([mm, qq]), "stats level %d #%d" % (level, i))
+
+
+def test_brute_hessian_bit_exact(fe, po, pair640, synth):
+    A, B = pair640
+    ga, gb = fe.make_pyramid(A, 6), fe.make_pyramid(B, 6)
+    oa, ob = po.Pyramid(A, 6), po.Pyramid(B, 6)
+    for level in (0, 2, 5):
+        w, h = oa.size(level)
+        pts = _features(synth, 200, h, w, seed=11 + level, border=0.3) if level < 5 else \
+            np.random.default_rng(1).uniform(0.5, [w - 0.5, h - 0.5], (200, 2)).astype(np.float32)
+        xy = pts + np.random.default_rng(2).uniform(-1.5, 1.5, pts.shape).astype(np.float32)
+        xy = np.clip(xy, 0.02, [w - 0.02, h - 0.02]).astype(np.float32)
+        out = fe.brute_hessian(ga, gb, level, pts, xy)
+        for i in range(len(pts)):
+            d, m, q = po.hes_get_patch(oa, level, pts[i, 0], pts[i, 1])
+            s0, d6 = po.hes_brute_hessian(ob, level, d, m, q, xy[i, 0], xy[i, 1])
+            assert_bits_equal(out[i], np.concatenate([[s0], d6]).astype(np.float32), "BruteHessian level %d #%d" % (level, i))
+
+
+@pytest.mark.parametrize("levels", [3, 6, "mixed"])
+def test_track_fb_bit_exact(fe, po, pair640, synth, levels):
+    A, B = pair640
+    H, W = A.shape[:2]
+    n = 600
+    pts = _features(synth, n, H, W)
+    if levels == "mixed":
+        lv = np.where(np.arange(n) % 3 == 0, 6, 3).astype(np.int32)
+    else:
+        lv = levels
+    ga, gb = fe.make_pyramid(A, 6), fe.make_pyramid(B, 6)
+    oa, ob = po.Pyramid(A, 6), po.Pyramid(B, 6)
+    g = fe.track_fb(ga, gb, pts, pts, lv)
+    o = po.hes_track_fb(oa, ob, pts, pts, lv)
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(g[k], o[k]), k
+    assert_bits_equal(g["to_xy"], o["to_xy"], "to_xy")
+    assert_bits_equal(g["back_xy"], o["back_xy"], "back_xy")
+    assert int(g["steps"].sum()) == o["newton_steps"]
+    assert np.abs(g["to_xy"] - o["to_xy"]).max() <= 1e-3          # north_star tolerance
+    assert g["accepted"].sum() > 0.8 * n * 0.8                    # the synthetic pair is trackable
+    truth = synth.true_motion(pts, H, W, 0.004, (1.7, -2.3))
+    err = np.linalg.norm(g["to_xy"] - truth, axis=1)[g["accepted"] == 1]
+    assert np.median(err) < 0.1
+
+
+def test_track_fb_batched_pairs(fe, po, synth):
+    """n_per_pair batching: 3 independent pairs in one call == three single-pair oracle runs."""
+    H, W = 240, 320
+    A, B = synth.make_pairs(21, 3, H, W)
+    A, B = A.numpy(), B.numpy()
+    npp = 150
+    pts = np.concatenate([_features(synth, npp, H, W, seed=30 + p) for p in range(3)])
+    ga, gb = fe.make_pyramid(A, 4), fe.make_pyramid(B, 4)
+    g = fe.track_fb(ga, gb, pts, pts, 4, n_per_pair=npp)
+    for p in range(3):
+        oa, ob = po.Pyramid(A[p], 4), po.Pyramid(B[p], 4)
+        sl = slice(p * npp, (p + 1) * npp)
+        o = po.hes_track_fb(oa, ob, pts[sl], pts[sl], 4)
+        assert np.array_equal(g["accepted"][sl], o["accepted"])
+        assert_bits_equal(g["to_xy"][sl], o["to_xy"], "pair %d to_xy" % p)
+        assert_bits_equal(g["back_xy"][sl], o["back_xy"], "pair %d back_xy" % p)
+
+
+def test_track_fb_empty_and_errors(fe, sfe, pair640):
+    A, _ = pair640
+    ga = fe.make_pyramid(A, 3)
+    g = fe.track_fb(ga, ga, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), 3)
+    assert g["to_xy"].shape == (0, 2)
+    kp = fe.make_pyramid(A, 3, flavor=sfe.KLT)
+    with pytest.raises(sfe.SlamFEError):
+        fe.track_fb(kp, kp, np.ones((4, 2), np.float32), np.ones((4, 2), np.float32), 3)
+    # identical frames: every interior feature must come back to where it started
+    pts = np.float32([[100.25, 200.5], [320, 240], [600.75, 30.125]])
+    g = fe.track_fb(ga, ga, pts, pts, 3)
+    assert g["accepted"].all() and np.abs(g["to_xy"] - pts).max() < 1e-2
+
+
+def test_klt_pyramid_and_track_bit_exact(fe, po, sfe, synth):
+    H, W = 240, 320
+    A, B = synth.make_pairs(4, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    n = 200
+    pts = _features(synth, n, H, W, seed=9, border=0.1)
+    ga, gb = fe.make_pyramid(A, 4, sfe.KLT), fe.make_pyramid(B, 4, sfe.KLT)
+    oa, ob = po.Pyramid(A, 4, po.FLAVOR_KLT), po.Pyramid(B, 4, po.FLAVOR_KLT)
+    g = fe.klt_track_fb(ga, gb, pts, pts)
+    o = po.klt_track_fb(oa, ob, pts, pts)
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(g[k], o[k]), k
+    assert_bits_equal(g["to_xy"], o["to_xy"], "klt to_xy")
+    assert_bits_equal(g["back_xy"], o["back_xy"], "klt back_xy")
+    assert int(g["steps"].sum()) == o["newton_steps"]
+    # the symmetric-KLT normal equations (klt.h:286-353)
+    xy = (pts + np.float32([0.4, -0.3])).astype(np.float32)
+    for level in (0, 2):
+        s = np.float32(0.5 ** level)
+        sysg = fe.klt_system(ga, gb, level, pts * s, xy * s)
+        for i in range(n):
+            ref = po.klt_system(oa, pts[i, 0] * s, pts[i, 1] * s, ob, level, xy[i, 0] * s, xy[i, 1] * s)
+            assert_bits_equal(sysg[i], ref, "klt system level %d #%d" % (level, i))
+
+
+def test_brute_track_bit_exact(fe, po, sfe, synth):
+    H, W = 240, 320
+    A, B = synth.make_pairs(6, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    n = 48
+    pts = synth.make_features(13, n, H, W, margin=20)
+    pts[:4] = [[5, 100], [100, 8], [W - 6, 100], [100, H - 5]]  # inside the margin-13 band -> OUT_OF_BOUNDS
+    ga, gb = fe.make_pyramid(A, 3, sfe.BRUTE), fe.make_pyramid(B, 3, sfe.BRUTE)
+    oa, ob = po.Pyramid(A, 3, po.FLAVOR_BRUTE), po.Pyramid(B, 3, po.FLAVOR_BRUTE)
+    g = fe.brute_track(ga, gb, pts, pts)
+    o = po.brute_track(oa, ob, pts, pts)
+    assert np.array_equal(g["status"], o["status"])
+    assert_bits_equal(g["to_xy"], o["to_xy"], "brute to_xy")
+    assert_bits_equal(g["best_sad"], o["best_sad"], "brute best_sad")
+    assert g["positions"] == o["positions"]
+    truth = synth.true_motion(pts, H, W, 0.004, (1.7, -2.3))
+    ok = g["status"] == 0
+    assert ok.sum() >= n - 8 and np.median(np.linalg.norm(g["to_xy"] - truth, axis=1)[ok]) < 0.15
+
+
+@pytest.mark.parametrize("nq,nt,batch", [(2000, 2000, 1), (777, 1301, 3), (1, 1, 1), (5, 0, 1), (300, 1, 2), (4096, 70000, 1)])
+def test_hamming_bit_exact(fe, po, synth, nq, nt, batch):
+    t = synth.make_descriptors(1, max(nt * batch, 1), dup_frac=0.05)[:nt * batch]
+    q = synth.make_descriptors(2, nq * batch, dup_frac=0.3, source=t if nt else None)
+    idx, dist, ok = fe.match_hamming256(q, t, 4, 5, 80, batch=batch)
+    for b in range(batch):
+        oi, od, oo = po.hamming256_top2(q[b * nq:(b + 1) * nq], t[b * nt:(b + 1) * nt], 4, 5, 80)
+        sl = slice(b * nq, (b + 1) * nq)
+        assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od) and np.array_equal(ok[sl], oo)
