@@ -9,9 +9,8 @@ __global__ void get_patches_kernel(PyrView v, int frame, int level, int n, const
                                    float* __restrict__ patches, float* __restrict__ mean, float* __restrict__ sumsq) {
   const int lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
-  const LanePix lp = lane_pix(lane);
   float T[SFE_SLOTS], m, q;
-  template_patch<MODE_HESSIAN>(img_of(v, 0, level, frame), xy[2 * i], xy[2 * i + 1], lp, T, m, q);
+  template_patch<MODE_HESSIAN>(img_of(v, 0, level, frame), xy[2 * i], xy[2 * i + 1], lane, T, m, q);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
     if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = T[k];
@@ -23,16 +22,15 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
                                                                        int level, int n, const float* __restrict__ txy,
                                                                        const float* __restrict__ xy, float* __restrict__ out7,
                                                                        const float* __restrict__ mask) {
-  __shared__ float tiles[TRK_WARPS][TILE];
+  __shared__ WarpScratch scratch[TRK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * TRK_WARPS + warp;
   if (i >= n) return;
-  const LanePix lp = lane_pix(lane);
   float mk[SFE_SLOTS];
   load_mask(mask, lane, mk);
   float T[SFE_SLOTS], m, q, d[6];
-  template_patch<MODE_HESSIAN>(img_of(tv, 0, level, tframe), txy[2 * i], txy[2 * i + 1], lp, T, m, q);
-  float s0 = brute_hessian<MODE_HESSIAN>(tiles[warp], img_of(sv, 0, level, sframe), T, m, q, mk, lp, xy[2 * i],
+  template_patch<MODE_HESSIAN>(img_of(tv, 0, level, tframe), txy[2 * i], txy[2 * i + 1], lane, T, m, q);
+  float s0 = brute_hessian<MODE_HESSIAN>(scratch[warp], img_of(sv, 0, level, sframe), T, m, q, mk, xy[2 * i],
                                          xy[2 * i + 1], lane, d);
   if (lane == 0) {
     out7[7 * i] = s0;

@@ -10,7 +10,16 @@
 // patches from global memory per Newton step.  Here the six patches share ONE 16x16 footprint
 // (origin floor(x)-7: the shifts never leave it), staged once per step in shared memory with
 // replicate clamping applied at load time; in the common case all six shifts also share their
-// integer taps, so every patch pixel loads its 4 taps once and evaluates six weight sets.
+// integer taps, so every lane loads the 4 taps of its patch pixels once (24 registers) and a
+// compact runtime loop over the six shifts evaluates weights, patch statistics and score.
+//
+// Code size matters as much as instruction count here: every warp sits at a different point of
+// a long dependent chain, so the kernel body must stay inside the instruction cache (the first
+// version, fully unrolled over shifts and inlined twice for forward/backward, was 157 KB of SASS
+// and spent >90% of its issue slots waiting for instructions; profiles/README.md).  Hence: one
+// direction loop, one level loop, one shift loop, lane-parallel geometry (lane j evaluates axis
+// variant j) and lane-parallel finite differences (lane j evaluates quotient j, so the thirteen
+// IEEE double divisions of BruteHessian cost three division sequences per warp).
 #pragma once
 #include "patch.cuh"
 
@@ -28,7 +37,14 @@ enum { MODE_HESSIAN = 0, MODE_KLT = 1 };
 
 constexpr int TRK_WARPS = 4;
 constexpr int TS = 16;  // tile row stride (floats)
-constexpr int TILE = 16 * TS;
+
+// per-warp shared scratch
+struct WarpScratch {
+  float tile[16 * TS];
+  float a[2][3], a1[2][3];  // [axis][variant] fractional weights
+  int i0[2][3], r[2][3];    // [axis][variant] integer origin / clipped entries
+  float score[8];
+};
 
 struct TileFetch {
   const float* t;
@@ -36,214 +52,157 @@ struct TileFetch {
   __device__ __forceinline__ float operator()(int Y, int X) const { return t[(Y - oy) * TS + (X - ox)]; }
 };
 
-// Stage the 16x16 footprint around (x,y) with coordinates clamped to the image (replicate).
-__device__ __forceinline__ void load_tile(float* tile, const ImgView& im, int ox, int oy, int lane) {
-  const int col = clampi(ox + (lane & 15), 0, im.w - 1);
-  const int rsub = lane >> 4;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int row = clampi(oy + 2 * j + rsub, 0, im.h - 1);
-    tile[(2 * j + rsub) * TS + (lane & 15)] = __ldg(im.p + (long long)row * im.pitch + col);
-  }
-}
+// shift s of BruteHessian uses x-variant (SXP >> 2s) & 3 and y-variant (SYP >> 2s) & 3
+//   hessian variants: 0 -> p, 1 -> p-h, 2 -> p+h;  shifts (0,0) (-h,0) (0,-h) (+h,0) (0,+h) (+h,+h)
+//   klt     variants: 0 -> p, 1 -> p+h, 2 -> p+2h; shifts (0,0) (h,0) (0,h) (2h,0) (0,2h) (h,h)
+template <int MODE>
+struct Shifts {
+  static constexpr unsigned SXP = MODE == MODE_HESSIAN ? (0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 2u << 10)
+                                                       : (0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 1u << 10);
+  static constexpr unsigned SYP = MODE == MODE_HESSIAN ? (0u | 0u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 2u << 10)
+                                                       : (0u | 0u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 1u << 10);
+};
 
-// per-lane partial of hessian.h:129-141 for one candidate patch
-__device__ __forceinline__ float score_partial_hessian(const float (&T)[SFE_SLOTS], const float (&v)[SFE_SLOTS],
-                                                       const float (&mk)[SFE_SLOTS], float alpha, float beta) {
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < SFE_SLOTS; ++k) {
-    float diff = fmaf(-v[k], alpha, T[k]) - beta;
-    diff = diff * diff;
-    float t = fmaf(diff, mk[k], s);
-    s = (T[k] == 0.f || v[k] == 0.f) ? s : t;
-  }
-  return s;
-}
-
-// per-lane partial of klt.h:139-149
-__device__ __forceinline__ float score_partial_klt(const float (&T)[SFE_SLOTS], const float (&v)[SFE_SLOTS],
-                                                   const float (&mk)[SFE_SLOTS]) {
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < SFE_SLOTS; ++k) {
-    float diff = T[k] - v[k];
-    float t = fmaf(diff * diff, mk[k], s);
-    s = (T[k] == 0.f || v[k] == 0.f) ? s : t;
-  }
-  return s;
+// Finite differences of the six scores, lane-parallel.  Stage A: lane j < NA forms
+// q_j = [0.5 *] (score[P_j] - score[M_j]) / h; stage B: lane j < 4 forms (q[PB_j] - q[MB_j]) / h.
+// All arithmetic is IEEE double, operation for operation what hessian.h:163-169 / klt.h:197-203
+// evaluate.  Returns d[6] = dx,dy,dxx,dxy,dyx,dyy in every lane.
+template <int MODE>
+__device__ __forceinline__ void finite_differences(const float* score, int lane, float (&d)[6]) {
+  // nibble tables indexed by lane
+  constexpr unsigned PA = MODE == MODE_HESSIAN ? 0x55040343u : 0x00554321u;  // P_j (j = 0 is the low nibble)
+  constexpr unsigned MA = MODE == MODE_HESSIAN ? 0x34201021u : 0x00122100u;  // M_j
+  constexpr unsigned PB = MODE == MODE_HESSIAN ? 0x7642u : 0x5432u;          // dxx,dyy,dxy,dyx minuend lane
+  constexpr unsigned MB = MODE == MODE_HESSIAN ? 0x4253u : 0x1010u;          // subtrahend lane
+  const double h = MODE == MODE_HESSIAN ? 0.02 : 0.01;
+  const int j = lane & 7;
+  const double p = (double)score[(PA >> (4 * j)) & 7], m = (double)score[(MA >> (4 * j)) & 7];
+  double num = __dsub_rn(p, m);
+  if (MODE == MODE_HESSIAN && j < 2) num = __dmul_rn(0.5, num);
+  const double q = __ddiv_rn(num, h);
+  const int jb = lane & 3;
+  const double qp = __shfl_sync(SFE_FULL, q, (PB >> (4 * jb)) & 7), qm = __shfl_sync(SFE_FULL, q, (MB >> (4 * jb)) & 7);
+  const double r = __ddiv_rn(__dsub_rn(qp, qm), h);
+  const float qf = (float)q, rf = (float)r;
+  d[0] = __shfl_sync(SFE_FULL, qf, 0);
+  d[1] = __shfl_sync(SFE_FULL, qf, 1);
+  d[2] = __shfl_sync(SFE_FULL, rf, 0);
+  d[5] = __shfl_sync(SFE_FULL, rf, 1);
+  d[3] = __shfl_sync(SFE_FULL, rf, 2);
+  d[4] = __shfl_sync(SFE_FULL, rf, 3);
 }
 
 // BruteHessian at (x,y): the six derivatives d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as
 // the reference stores them through float*); returns sad0.
 template <int MODE>
-__device__ __forceinline__ float brute_hessian(float* tile, const ImgView& im, const float (&T)[SFE_SLOTS],
-                                               float tmean, float tsumsq, const float (&mk)[SFE_SLOTS],
-                                               const LanePix& lp, float x, float y, int lane, float (&d)[6]) {
+__device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im, const float (&T)[SFE_SLOTS],
+                                            float tmean, float tsumsq, const float (&mk)[SFE_SLOTS], float x, float y,
+                                            int lane, float (&d)[6]) {
   constexpr bool CLIP = MODE == MODE_HESSIAN;
-  // shifted coordinates are formed in double and rounded to float (cv::Point2f(pt.x - h, pt.y))
-  float xs[3], ys[3];
-  xs[0] = x;
-  ys[0] = y;
-  if (MODE == MODE_HESSIAN) {  // x, x-h, x+h with h = 0.02
-    xs[1] = (float)((double)x - 0.02); xs[2] = (float)((double)x + 0.02);
-    ys[1] = (float)((double)y - 0.02); ys[2] = (float)((double)y + 0.02);
-  } else {                     // x, x+h, x+2h with h = 0.01 (2*h == 0.02 exactly as doubles)
-    xs[1] = (float)((double)x + 0.01); xs[2] = (float)((double)x + 0.02);
-    ys[1] = (float)((double)y + 0.01); ys[2] = (float)((double)y + 0.02);
+  __syncwarp();
+  // ---- geometry, lane-parallel: lane j < 3 evaluates x-variant j and y-variant j.  Shifted
+  // coordinates are formed in double and rounded to float (cv::Point2f(pt.x - h, pt.y)).
+  if (lane < 3) {
+    const double off = MODE == MODE_HESSIAN ? (lane == 0 ? 0.0 : (lane == 1 ? -0.02 : 0.02))
+                                            : (lane == 0 ? 0.0 : (lane == 1 ? 0.01 : 0.02));
+    const float xs = lane == 0 ? x : (float)((double)x + off), ys = lane == 0 ? y : (float)((double)y + off);
+    const AxisGeom gx = axis_geom(xs, CLIP, true), gy = axis_geom(ys, CLIP, false);
+    S.a[0][lane] = gx.a; S.a1[0][lane] = gx.a1; S.i0[0][lane] = gx.i0; S.r[0][lane] = gx.r;
+    S.a[1][lane] = gy.a; S.a1[1][lane] = gy.a1; S.i0[1][lane] = gy.i0; S.r[1][lane] = gy.r;
   }
-  AxisGeom gx[3], gy[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    gx[j] = axis_geom(xs[j], CLIP, true);
-    gy[j] = axis_geom(ys[j], CLIP, false);
-  }
-  // shift s uses x-variant SX[s], y-variant SY[s]
-  //   hessian: (0,0) (-h,0) (0,-h) (+h,0) (0,+h) (+h,+h)     klt: (0,0) (h,0) (0,h) (2h,0) (0,2h) (h,h)
-  constexpr int SX[6] = {0, 1, 0, 2, 0, MODE == MODE_HESSIAN ? 2 : 1};
-  constexpr int SY[6] = {0, 0, 1, 0, 2, MODE == MODE_HESSIAN ? 2 : 1};
-
+  // ---- stage the 16x16 footprint (replicate-clamped)
   const int ox = (int)floorf(x) - 7, oy = (int)floorf(y) - 7;
-  __syncwarp();
-  load_tile(tile, im, ox, oy, lane);
-  __syncwarp();
-
-  float v[6][SFE_SLOTS];
-  const bool same = gx[1].i0 == gx[0].i0 && gx[2].i0 == gx[0].i0 && gy[1].i0 == gy[0].i0 && gy[2].i0 == gy[0].i0;
-  const bool noclip = (gx[0].r | gx[1].r | gx[2].r | gy[0].r | gy[1].r | gy[2].r) == 0;
-  const bool interior = gx[0].i0 >= 0 && gx[0].i0 + SFE_PATCH <= im.w - 1 && gy[0].i0 >= 0 &&
-                        gy[0].i0 + SFE_PATCH <= im.h - 1;
-  if (same && noclip && interior) {
-    // fast path: every patch pixel reads its 4 taps once; six weight sets
-    float w[6][4];
+  {
+    const int col = clampi(ox + (lane & 15), 0, im.w - 1);
+    const int rsub = lane >> 4;
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const AxisGeom &ax = gx[SX[s]], &ay = gy[SY[s]];
-      w[s][0] = ax.a1 * ay.a1; w[s][1] = ax.a * ay.a1; w[s][2] = ax.a1 * ay.a; w[s][3] = ax.a * ay.a;
+    for (int j = 0; j < 8; ++j) {
+      const int row = clampi(oy + 2 * j + rsub, 0, im.h - 1);
+      S.tile[(2 * j + rsub) * TS + (lane & 15)] = __ldg(im.p + (long long)row * im.pitch + col);
     }
-    const int base = (gy[0].i0 - oy) * TS + (gx[0].i0 - ox);
+  }
+  __syncwarp();
+  const int ix = S.i0[0][0], iy = S.i0[1][0];
+  const bool same = S.i0[0][1] == ix && S.i0[0][2] == ix && S.i0[1][1] == iy && S.i0[1][2] == iy;
+  const bool noclip = (S.r[0][0] | S.r[0][1] | S.r[0][2] | S.r[1][0] | S.r[1][1] | S.r[1][2]) == 0;
+  const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
+  const bool fast = same && noclip && interior;
+
+  float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
+  if (fast) {  // every patch pixel reads its 4 taps once, shared by the six shifts
+    const float* t0 = S.tile + (iy - oy) * TS + (ix - ox);
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
-      if (lp.pr[k] < SFE_PATCH) {
-        const float* t = tile + base + lp.pr[k] * TS + lp.pc[k];
-        float s00 = t[0], s01 = t[1], s10 = t[TS], s11 = t[TS + 1];
-#pragma unroll
-        for (int s = 0; s < 6; ++s) v[s][k] = fmaf(s11, w[s][3], fmaf(s10, w[s][2], fmaf(s01, w[s][1], s00 * w[s][0])));
-      } else {
-#pragma unroll
-        for (int s = 0; s < 6; ++s) v[s][k] = 0.f;
-      }
+      const int i = lane + 32 * k;
+      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+      const bool valid = i < SFE_PLEN;
+      const float* t = t0 + (valid ? pr * TS + pc : 0);
+      t00[k] = valid ? t[0] : 0.f;
+      t01[k] = valid ? t[1] : 0.f;
+      t10[k] = valid ? t[TS] : 0.f;
+      t11[k] = valid ? t[TS + 1] : 0.f;
     }
-  } else {
-    TileFetch f{tile, ox, oy};
+  }
+
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    const int jx = (Shifts<MODE>::SXP >> (2 * s)) & 3, jy = (Shifts<MODE>::SYP >> (2 * s)) & 3;
+    const float ax = S.a[0][jx], ax1 = S.a1[0][jx], ay = S.a[1][jy], ay1 = S.a1[1][jy];
+    float v[SFE_SLOTS];
+    if (fast) {
+      const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const AxisGeom ax = gx[SX[s]], ay = gy[SY[s]];
+      for (int k = 0; k < SFE_SLOTS; ++k) v[k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+    } else {
+      const TileFetch f{S.tile, ox, oy};
+      const int x0 = S.i0[0][jx], rx = S.r[0][jx], y0 = S.i0[1][jy], ry = S.r[1][jy];
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
-        bool valid = lp.pr[k] < SFE_PATCH && lp.pr[k] >= ay.r && lp.pc[k] >= ax.r;
+        const int i = lane + 32 * k;
+        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
         float r = 0.f;
-        if (valid) r = sample_general(f, ax.i0 + lp.pc[k], ay.i0 + lp.pr[k], im.w, im.h, ax.a, ax.a1, ay.a, ay.a1);
-        v[s][k] = r;
+        if (i < SFE_PLEN && pr >= ry && pc >= rx) r = sample_general(f, x0 + pc, y0 + pr, im.w, im.h, ax, ax1, ay, ay1);
+        v[k] = r;
       }
     }
-  }
-
-  double sc[6];
-#pragma unroll
-  for (int s = 0; s < 6; ++s) {
-    if (MODE == MODE_HESSIAN) {
+    float part = 0.f;
+    if (MODE == MODE_HESSIAN) {  // hessian.h:129-141
       float m, q;
-      patch_stats(v[s], m, q);
-      float alpha = sqrtf(tsumsq / q);
-      float beta = tmean - alpha * m;
-      sc[s] = (double)warp_sum(score_partial_hessian(T, v[s], mk, alpha, beta));
-    } else {
-      sc[s] = (double)warp_sum(score_partial_klt(T, v[s], mk));
+      patch_stats(v, m, q);
+      const float alpha = sqrtf(tsumsq / q);
+      const float beta = tmean - alpha * m;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        float diff = fmaf(-v[k], alpha, T[k]) - beta;
+        diff = diff * diff;
+        const float t = fmaf(diff, mk[k], part);
+        part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
+      }
+    } else {  // klt.h:139-149
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const float diff = T[k] - v[k];
+        const float t = fmaf(diff * diff, mk[k], part);
+        part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
+      }
     }
+    const float sc = warp_sum(part);
+    if (lane == 0) S.score[s] = sc;
   }
-  if (MODE == MODE_HESSIAN) {  // hessian.h:154-169
-    const double h = 0.02;
-    const double sad0 = sc[0], sadn1x = sc[1], sadn1y = sc[2], sadp1x = sc[3], sadp1y = sc[4], sadxy = sc[5];
-    const double A = __ddiv_rn(__dsub_rn(sadp1x, sad0), h), B = __ddiv_rn(__dsub_rn(sad0, sadn1x), h);
-    const double C = __ddiv_rn(__dsub_rn(sadp1y, sad0), h), D = __ddiv_rn(__dsub_rn(sad0, sadn1y), h);
-    d[0] = (float)__ddiv_rn(__dmul_rn(0.5, __dsub_rn(sadp1x, sadn1x)), h);
-    d[1] = (float)__ddiv_rn(__dmul_rn(0.5, __dsub_rn(sadp1y, sadn1y)), h);
-    d[2] = (float)__ddiv_rn(__dsub_rn(A, B), h);
-    d[5] = (float)__ddiv_rn(__dsub_rn(C, D), h);
-    d[3] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadxy, sadp1y), h), A), h);
-    d[4] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadxy, sadp1x), h), C), h);
-  } else {  // klt.h:188-203
-    const double h = 0.01;
-    const double sad0 = sc[0], sadx = sc[1], sady = sc[2], sadxx = sc[3], sadyy = sc[4], sadxy = sc[5];
-    const double A = __ddiv_rn(__dsub_rn(sadx, sad0), h), C = __ddiv_rn(__dsub_rn(sady, sad0), h);
-    d[0] = (float)A;
-    d[1] = (float)C;
-    d[2] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadxx, sadx), h), A), h);
-    d[5] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadyy, sady), h), C), h);
-    d[3] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadxy, sady), h), A), h);
-    d[4] = (float)__ddiv_rn(__dsub_rn(__ddiv_rn(__dsub_rn(sadxy, sadx), h), C), h);
-  }
-  return (float)sc[0];
+  __syncwarp();
+  finite_differences<MODE>(S.score, lane, d);
+  return S.score[0];
 }
 
-// Track (hessian.h:185-241 / klt.h:258-401)
+// GetPatch of the template (hessian.h:54-93 / klt.h:59-96, image plane) straight from global memory
 template <int MODE>
-__device__ __forceinline__ int track_level(float* tile, const ImgView& im, const float (&T)[SFE_SLOTS], float tmean,
-                                           float tsumsq, const float (&mk)[SFE_SLOTS], const LanePix& lp,
-                                           float threshold, int maxit, float& x, float& y, int lane, int& steps) {
-  const float margin = MODE == MODE_HESSIAN ? 0.01f : 0.1f;
-  for (int it = 0; it < maxit; ++it) {
-    if (x < margin || y < margin || (x + margin) > (float)im.w || (y + margin) > (float)im.h) return SFE_OUT_OF_BOUNDS;
-    float d[6];
-    brute_hessian<MODE>(tile, im, T, tmean, tsumsq, mk, lp, x, y, lane, d);
-    ++steps;
-    float dx, dy;
-    newton_step(d[0], d[1], d[2], d[3], d[4], d[5], dx, dy);
-    x += clamp1(dx);
-    y += clamp1(dy);
-    if (MODE == MODE_HESSIAN) {
-      if (fabsf(dx) < threshold && fabsf(dy) < threshold) break;
-    } else {  // klt.h:392: float |d| against the double threshold/10.
-      const double t10 = __ddiv_rn((double)threshold, 10.0);
-      if ((double)fabsf(dx) < t10 && (double)fabsf(dy) < t10) break;
-    }
-  }
-  return SFE_OK;
-}
-
-template <int MODE>
-__device__ __forceinline__ void template_patch(const ImgView& tim, float tx, float ty, const LanePix& lp,
-                                               float (&T)[SFE_SLOTS], float& tmean, float& tsumsq) {
+__device__ __forceinline__ void template_patch(const ImgView tim, float tx, float ty, int lane, float (&T)[SFE_SLOTS],
+                                            float& tmean, float& tsumsq) {
   PatchGeom g;
   g.x = axis_geom(tx, MODE == MODE_HESSIAN, true);
   g.y = axis_geom(ty, MODE == MODE_HESSIAN, false);
-  sample_patch_global(tim, g, lp, T);
+  sample_patch_global(tim, g, lane_pix(lane), T);
   patch_stats(T, tmean, tsumsq);
-}
-
-// GetPatches (hessian.h:175-183 / klt.h:249-256) on the template pyramid + TrackFeature
-// (hessian.h:243-264 / klt.h:403-424) on the search pyramid.  (x,y) is updated only on success.
-template <int MODE>
-__device__ __forceinline__ int track_feature(float* tile, const PyrView& tp, int tframe, float tx, float ty,
-                                             const PyrView& sp, int sframe, int levels, float thr, int maxit,
-                                             const float (&mk)[SFE_SLOTS], const LanePix& lp, float& x, float& y,
-                                             int lane, int& steps) {
-  int lv = min(tp.depth, sp.depth);
-  if (MODE == MODE_HESSIAN) lv = min(lv, levels);
-  float px = x * (float)(1. / (1 << (lv - 1))), py = y * (float)(1. / (1 << (lv - 1)));
-  for (int i = lv - 1; i >= 0; --i) {
-    const float sc = (float)(1. / (1 << i));  // pt *= 0.5 i times (exact)
-    float T[SFE_SLOTS], tmean, tsumsq;
-    template_patch<MODE>(img_of(tp, 0, i, tframe), tx * sc, ty * sc, lp, T, tmean, tsumsq);
-    const float th = (MODE == MODE_KLT && i > 0) ? thr * 50.f : thr;  // klt.h:413
-    int st = track_level<MODE>(tile, img_of(sp, 0, i, sframe), T, tmean, tsumsq, mk, lp, th, maxit, px, py, lane, steps);
-    if (st != SFE_OK) return st;
-    if (i > 0) { px *= 2.f; py *= 2.f; }
-  }
-  x = px;
-  y = py;
-  return SFE_OK;
 }
 
 __device__ __forceinline__ void load_mask(const float* __restrict__ mask, int lane, float (&mk)[SFE_SLOTS]) {
@@ -251,15 +210,56 @@ __device__ __forceinline__ void load_mask(const float* __restrict__ mask, int la
   for (int k = 0; k < SFE_SLOTS; ++k) mk[k] = (lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
 }
 
+// GetPatches (hessian.h:175-183 / klt.h:249-256) on the template pyramid + TrackFeature
+// (hessian.h:243-264 / klt.h:403-424) with Track (hessian.h:185-241 / klt.h:258-401) on the search
+// pyramid.  (x,y) is updated only on success.
+template <int MODE>
+__device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, int tframe, float tx, float ty,
+                                             const PyrView& sp, int sframe, int levels, float thr, int maxit,
+                                             const float (&mk)[SFE_SLOTS], float& x, float& y, int lane, int& steps) {
+  int lv = min(tp.depth, sp.depth);
+  if (MODE == MODE_HESSIAN) lv = min(lv, levels);
+  const float margin = MODE == MODE_HESSIAN ? 0.01f : 0.1f;
+  float px = x * (float)(1. / (1 << (lv - 1))), py = y * (float)(1. / (1 << (lv - 1)));
+#pragma unroll 1
+  for (int i = lv - 1; i >= 0; --i) {
+    const float sc = (float)(1. / (1 << i));  // pt *= 0.5 i times (exact)
+    float T[SFE_SLOTS], tmean, tsumsq;
+    template_patch<MODE>(img_of(tp, 0, i, tframe), tx * sc, ty * sc, lane, T, tmean, tsumsq);
+    const float th = (MODE == MODE_KLT && i > 0) ? thr * 50.f : thr;  // klt.h:413
+    const ImgView im = img_of(sp, 0, i, sframe);
+#pragma unroll 1
+    for (int it = 0; it < maxit; ++it) {
+      if (px < margin || py < margin || (px + margin) > (float)im.w || (py + margin) > (float)im.h) return SFE_OUT_OF_BOUNDS;
+      float d[6];
+      brute_hessian<MODE>(S, im, T, tmean, tsumsq, mk, px, py, lane, d);
+      ++steps;
+      float dx, dy;
+      newton_step(d[0], d[1], d[2], d[3], d[4], d[5], dx, dy);
+      px += clamp1(dx);
+      py += clamp1(dy);
+      if (MODE == MODE_HESSIAN) {
+        if (fabsf(dx) < th && fabsf(dy) < th) break;
+      } else {  // klt.h:392: float |d| against the double threshold/10.
+        const double t10 = __ddiv_rn((double)th, 10.0);
+        if ((double)fabsf(dx) < t10 && (double)fabsf(dy) < t10) break;
+      }
+    }
+    if (i > 0) { px *= 2.f; py *= 2.f; }
+  }
+  x = px;
+  y = py;
+  return SFE_OK;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(32 * TRK_WARPS) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
                                                                   const float* __restrict__ mask) {
-  __shared__ float tiles[TRK_WARPS][TILE];
+  __shared__ WarpScratch scratch[TRK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * TRK_WARPS + warp;
   if (i >= a.n) return;
-  float* tile = tiles[warp];
-  const LanePix lp = lane_pix(lane);
+  WarpScratch& S = scratch[warp];
   float mk[SFE_SLOTS];
   load_mask(mask, lane, mk);
 
@@ -269,22 +269,31 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) track_fb_kernel(PyrView from, 
   float tx = a.to_xy[2 * i], ty = a.to_xy[2 * i + 1];
   const int lv = a.levels ? a.levels[i] : a.default_levels;
   int steps = 0;
-
-  int s1 = track_feature<MODE>(tile, from, ff, fx, fy, to, tf, lv, a.thr, a.maxit, mk, lp, tx, ty, lane, steps);  // :175-176
-  float bx = fx, by = fy;                                                                                        // :181
-  int s2 = track_feature<MODE>(tile, to, tf, tx, ty, from, ff, lv, a.thr, a.maxit, mk, lp, bx, by, lane, steps);  // :180-182
-  bool ok = !(s1 || s2);                                                                                         // :192
+  int st[2];
+  float bx = fx, by = fy;  // matcher.cpp:181
+  // dir 0: template from `from` at from_pt, search `to` from the seed (matcher.cpp:175-176)
+  // dir 1: template from `to` at the forward result, search `from` from from_pt (matcher.cpp:180-182)
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {
+    const PyrView& tp = dir == 0 ? from : to;
+    const PyrView& sp = dir == 0 ? to : from;
+    float x = dir == 0 ? tx : bx, y = dir == 0 ? ty : by;
+    const int s = track_feature<MODE>(S, tp, dir == 0 ? ff : tf, dir == 0 ? fx : tx, dir == 0 ? fy : ty, sp,
+                                      dir == 0 ? tf : ff, lv, a.thr, a.maxit, mk, x, y, lane, steps);
+    if (dir == 0) { tx = x; ty = y; st[0] = s; } else { bx = x; by = y; st[1] = s; }
+  }
+  bool ok = !(st[0] || st[1]);  // matcher.cpp:192
   if (ok) {
     float ddx = fx - bx, ddy = fy - by;
     double nrm = sqrt(__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)));
-    if (nrm > (double)a.fb_max) ok = false;                                                                      // :201
+    if (nrm > (double)a.fb_max) ok = false;  // matcher.cpp:201
   }
   if (lane == 0) {
     a.to_xy[2 * i] = tx;
     a.to_xy[2 * i + 1] = ty;
     if (a.back_xy) { a.back_xy[2 * i] = bx; a.back_xy[2 * i + 1] = by; }
-    if (a.status_fwd) a.status_fwd[i] = s1;
-    if (a.status_bwd) a.status_bwd[i] = s2;
+    if (a.status_fwd) a.status_fwd[i] = st[0];
+    if (a.status_bwd) a.status_bwd[i] = st[1];
     if (a.accepted) a.accepted[i] = ok ? 1 : 0;
     if (a.steps) a.steps[i] = steps;
   }
