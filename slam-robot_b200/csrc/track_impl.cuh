@@ -67,8 +67,9 @@ struct Shifts {
 // q_j = [0.5 *] (score[P_j] - score[M_j]) / h; stage B: lane j < 4 forms (q[PB_j] - q[MB_j]) / h.
 // All arithmetic is IEEE double, operation for operation what hessian.h:163-169 / klt.h:197-203
 // evaluate.  Returns d[6] = dx,dy,dxx,dxy,dyx,dyy in every lane.
+// `sc` holds score s in lanes 4s..4s+3 (the layout packed_reduce8 leaves).
 template <int MODE>
-__device__ __forceinline__ void finite_differences(const float* score, int lane, float (&d)[6]) {
+__device__ __forceinline__ void finite_differences(float sc, int lane, float (&d)[6]) {
   // nibble tables indexed by lane
   constexpr unsigned PA = MODE == MODE_HESSIAN ? 0x55040343u : 0x00554321u;  // P_j (j = 0 is the low nibble)
   constexpr unsigned MA = MODE == MODE_HESSIAN ? 0x34201021u : 0x00122100u;  // M_j
@@ -76,7 +77,8 @@ __device__ __forceinline__ void finite_differences(const float* score, int lane,
   constexpr unsigned MB = MODE == MODE_HESSIAN ? 0x4253u : 0x1010u;          // subtrahend lane
   const double h = MODE == MODE_HESSIAN ? 0.02 : 0.01;
   const int j = lane & 7;
-  const double p = (double)score[(PA >> (4 * j)) & 7], m = (double)score[(MA >> (4 * j)) & 7];
+  const double p = (double)__shfl_sync(SFE_FULL, sc, 4 * ((PA >> (4 * j)) & 7));
+  const double m = (double)__shfl_sync(SFE_FULL, sc, 4 * ((MA >> (4 * j)) & 7));
   double num = __dsub_rn(p, m);
   if (MODE == MODE_HESSIAN && j < 2) num = __dmul_rn(0.5, num);
   const double q = __ddiv_rn(num, h);
@@ -128,34 +130,93 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
   const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
   const bool fast = same && noclip && interior;
 
-  float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
-  if (fast) {  // every patch pixel reads its 4 taps once, shared by the six shifts
-    const float* t0 = S.tile + (iy - oy) * TS + (ix - ox);
+  float sc;  // score s in lanes 4s..4s+3
+  if (fast) {
+    // ---- fast path, fully unrolled: every patch pixel reads its 4 taps once; six weight sets
+    float v[6][SFE_SLOTS];
+    {
+      float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
+      const float* t0 = S.tile + (iy - oy) * TS + (ix - ox);
 #pragma unroll
-    for (int k = 0; k < SFE_SLOTS; ++k) {
-      const int i = lane + 32 * k;
-      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-      const bool valid = i < SFE_PLEN;
-      const float* t = t0 + (valid ? pr * TS + pc : 0);
-      t00[k] = valid ? t[0] : 0.f;
-      t01[k] = valid ? t[1] : 0.f;
-      t10[k] = valid ? t[TS] : 0.f;
-      t11[k] = valid ? t[TS + 1] : 0.f;
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const int i = lane + 32 * k;
+        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+        const bool valid = k < SFE_SLOTS - 1 || i < SFE_PLEN;
+        const float* t = t0 + (valid ? pr * TS + pc : 0);
+        t00[k] = valid ? t[0] : 0.f;
+        t01[k] = valid ? t[1] : 0.f;
+        t10[k] = valid ? t[TS] : 0.f;
+        t11[k] = valid ? t[TS + 1] : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const int jx = (Shifts<MODE>::SXP >> (2 * s)) & 3, jy = (Shifts<MODE>::SYP >> (2 * s)) & 3;
+        const float ax = S.a[0][jx], ax1 = S.a1[0][jx], ay = S.a[1][jy], ay1 = S.a1[1][jy];
+        const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+      }
     }
-  }
-
-#pragma unroll 1
-  for (int s = 0; s < 6; ++s) {
-    const int jx = (Shifts<MODE>::SXP >> (2 * s)) & 3, jy = (Shifts<MODE>::SYP >> (2 * s)) & 3;
-    const float ax = S.a[0][jx], ax1 = S.a1[0][jx], ay = S.a[1][jy], ay1 = S.a1[1][jy];
-    float v[SFE_SLOTS];
-    if (fast) {
-      const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
+    float part[8];
+    part[6] = part[7] = 0.f;
+    if (MODE == MODE_HESSIAN) {
+      // patch statistics of the six candidates (hessian.h:85-91): 12 sums in one packed reduction
+      float st[16];
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) v[k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+      for (int s = 0; s < 6; ++s) {
+        float sm = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) {
+          sm = sm + v[s][k];
+          sq = fmaf(v[s][k], v[s][k], sq);
+        }
+        st[s] = sm;
+        st[8 + s] = sq;
+      }
+      st[6] = st[7] = st[14] = st[15] = 0.f;
+      const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
+      const float other = __shfl_xor_sync(SFE_FULL, red, 16);
+      // lane-parallel alpha/beta (hessian.h:131-132): lanes 2s (s < 6) hold the values of shift s
+      const float mean = red / (float)SFE_PLEN, sumsq = other / (float)SFE_PLEN;
+      const float alpha_l = sqrtf(tsumsq / sumsq);
+      const float beta_l = tmean - alpha_l * mean;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
+        float p = 0.f;
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139
+          float diff = fmaf(-v[s][k], alpha, T[k]) - beta;
+          diff = diff * diff;
+          const float t = fmaf(diff, mk[k], p);
+          p = (T[k] == 0.f || v[s][k] == 0.f) ? p : t;
+        }
+        part[s] = p;
+      }
     } else {
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        float p = 0.f;
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) {  // klt.h:141-147
+          const float diff = T[k] - v[s][k];
+          const float t = fmaf(diff * diff, mk[k], p);
+          p = (T[k] == 0.f || v[s][k] == 0.f) ? p : t;
+        }
+        part[s] = p;
+      }
+    }
+    sc = packed_reduce8(part, lane);
+  } else {
+    // ---- general path (image borders, GetPatch clipping, a shift crossing an integer boundary):
+    // compact loop over the shifts, border rules of cv::getRectSubPix applied per tap
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+      const int jx = (Shifts<MODE>::SXP >> (2 * s)) & 3, jy = (Shifts<MODE>::SYP >> (2 * s)) & 3;
+      const float ax = S.a[0][jx], ax1 = S.a1[0][jx], ay = S.a[1][jy], ay1 = S.a1[1][jy];
       const TileFetch f{S.tile, ox, oy};
       const int x0 = S.i0[0][jx], rx = S.r[0][jx], y0 = S.i0[1][jy], ry = S.r[1][jy];
+      float v[SFE_SLOTS];
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
         const int i = lane + 32 * k;
@@ -164,34 +225,35 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
         if (i < SFE_PLEN && pr >= ry && pc >= rx) r = sample_general(f, x0 + pc, y0 + pr, im.w, im.h, ax, ax1, ay, ay1);
         v[k] = r;
       }
-    }
-    float part = 0.f;
-    if (MODE == MODE_HESSIAN) {  // hessian.h:129-141
-      float m, q;
-      patch_stats(v, m, q);
-      const float alpha = sqrtf(tsumsq / q);
-      const float beta = tmean - alpha * m;
+      float part = 0.f;
+      if (MODE == MODE_HESSIAN) {
+        float m, q;
+        patch_stats(v, m, q);
+        const float alpha = sqrtf(tsumsq / q);
+        const float beta = tmean - alpha * m;
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        float diff = fmaf(-v[k], alpha, T[k]) - beta;
-        diff = diff * diff;
-        const float t = fmaf(diff, mk[k], part);
-        part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
-      }
-    } else {  // klt.h:139-149
+        for (int k = 0; k < SFE_SLOTS; ++k) {
+          float diff = fmaf(-v[k], alpha, T[k]) - beta;
+          diff = diff * diff;
+          const float t = fmaf(diff, mk[k], part);
+          part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        const float diff = T[k] - v[k];
-        const float t = fmaf(diff * diff, mk[k], part);
-        part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
+        for (int k = 0; k < SFE_SLOTS; ++k) {
+          const float diff = T[k] - v[k];
+          const float t = fmaf(diff * diff, mk[k], part);
+          part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
+        }
       }
+      const float tot = warp_sum(part);
+      if (lane == 0) S.score[s] = tot;
     }
-    const float sc = warp_sum(part);
-    if (lane == 0) S.score[s] = sc;
+    __syncwarp();
+    sc = S.score[(lane >> 2) & 7];
   }
-  __syncwarp();
-  finite_differences<MODE>(S.score, lane, d);
-  return S.score[0];
+  finite_differences<MODE>(sc, lane, d);
+  return __shfl_sync(SFE_FULL, sc, 0);
 }
 
 // GetPatch of the template (hessian.h:54-93 / klt.h:59-96, image plane) straight from global memory
@@ -253,7 +315,7 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(32 * TRK_WARPS) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
+__global__ void __launch_bounds__(32 * TRK_WARPS, 4) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
                                                                   const float* __restrict__ mask) {
   __shared__ WarpScratch scratch[TRK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
