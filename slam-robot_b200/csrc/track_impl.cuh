@@ -41,6 +41,7 @@ constexpr int TS = 16;  // tile row stride (floats)
 // per-warp shared scratch
 struct WarpScratch {
   float tile[16 * TS];
+  float zero[TS + 2];       // taps of unused patch entries point here (must directly follow tile)
   float a[2][3], a1[2][3];  // [axis][variant] fractional weights
   int i0[2][3], r[2][3];    // [axis][variant] integer origin / clipped entries
   float score[8];
@@ -94,12 +95,15 @@ __device__ __forceinline__ void finite_differences(float sc, int lane, float (&d
   d[4] = __shfl_sync(SFE_FULL, rf, 3);
 }
 
-// BruteHessian at (x,y): the six derivatives d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as
-// the reference stores them through float*); returns sad0.
+// One patch evaluation at (x,y) of image `im`, two kinds sharing all of the sampling code:
+//   is_tmpl   GetPatch (hessian.h:54-93 / klt.h:59-96): T[] <- the patch, tmean/tsumsq <- its statistics
+//   otherwise BruteHessian (hessian.h:147-172 / klt.h:181-204) against the template T: the six
+//             derivatives d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as the reference stores them
+//             through float*); returns sad0.
 template <int MODE>
-__device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im, const float (&T)[SFE_SLOTS],
-                                            float tmean, float tsumsq, const float (&mk)[SFE_SLOTS], float x, float y,
-                                            int lane, float (&d)[6]) {
+__device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool is_tmpl, float (&T)[SFE_SLOTS],
+                                          float& tmean, float& tsumsq, const float (&mk)[SFE_SLOTS], float x, float y,
+                                          int lane, float (&d)[6]) {
   constexpr bool CLIP = MODE == MODE_HESSIAN;
   __syncwarp();
   // ---- geometry, lane-parallel: lane j < 3 evaluates x-variant j and y-variant j.  Shifted
@@ -157,6 +161,11 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
         for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
       }
     }
+    if (MODE == MODE_KLT && is_tmpl) {  // klt.h scoring does not use the template statistics
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) T[k] = v[0][k];
+      return 0.f;
+    }
     float part[8];
     part[6] = part[7] = 0.f;
     if (MODE == MODE_HESSIAN) {
@@ -177,8 +186,17 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
       const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
       const float other = __shfl_xor_sync(SFE_FULL, red, 16);
       // lane-parallel alpha/beta (hessian.h:131-132): lanes 2s (s < 6) hold the values of shift s
-      const float mean = red / (float)SFE_PLEN, sumsq = other / (float)SFE_PLEN;
-      const float alpha_l = sqrtf(tsumsq / sumsq);
+      // (lanes >= 12 hold padding: give them benign operands so the IEEE divide/sqrt stay on their fast paths)
+      const bool live = lane < 12;
+      const float mean = red / (float)SFE_PLEN, sumsq = live ? other / (float)SFE_PLEN : 1.f;
+      if (is_tmpl) {  // shift 0 is the patch itself: lane 0 holds its statistics
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) T[k] = v[0][k];
+        tmean = __shfl_sync(SFE_FULL, mean, 0);
+        tsumsq = __shfl_sync(SFE_FULL, sumsq, 0);
+        return 0.f;
+      }
+      const float alpha_l = sqrtf((live ? tsumsq : 1.f) / sumsq);
       const float beta_l = tmean - alpha_l * mean;
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
@@ -208,27 +226,64 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
     }
     sc = packed_reduce8(part, lane);
   } else {
-    // ---- general path (image borders, GetPatch clipping, a shift crossing an integer boundary):
-    // compact loop over the shifts, border rules of cv::getRectSubPix applied per tap
+    // ---- border path (image borders, GetPatch clipping, or a shift crossing an integer boundary).
+    // cv::getRectSubPix's border rules are per pixel: "full" 4-tap, "vertical" 2-tap (overflow
+    // column, and corners), "horizontal" 2-tap (overflow row).  With the unused taps zeroed and
+    // A1' = xin ? 1-a : 1, B1' = vert ? 1-b : 1 the weights (A1'B1', aB1', A1'b, ab) reproduce the
+    // rule exactly (x*1 is exact and a zero tap adds an exact zero), so one FMA chain serves all
+    // pixels.  Per patch pixel: one tile offset (entries that are clipped or beyond 169 point into the
+    // zero region behind the tile) and two bit masks; a compact runtime loop over the shifts.
+    const bool shared_geom = same && S.r[0][1] == S.r[0][0] && S.r[0][2] == S.r[0][0] && S.r[1][1] == S.r[1][0] &&
+                             S.r[1][2] == S.r[1][0];
+    int toff[SFE_SLOTS];
+    unsigned mx[SFE_SLOTS], mv[SFE_SLOTS];  // all-ones where the pixel uses x weights / vertical weights
+    const int nshift = is_tmpl ? 1 : 6;
 #pragma unroll 1
-    for (int s = 0; s < 6; ++s) {
+    for (int s = 0; s < nshift; ++s) {
       const int jx = (Shifts<MODE>::SXP >> (2 * s)) & 3, jy = (Shifts<MODE>::SYP >> (2 * s)) & 3;
-      const float ax = S.a[0][jx], ax1 = S.a1[0][jx], ay = S.a[1][jy], ay1 = S.a1[1][jy];
-      const TileFetch f{S.tile, ox, oy};
-      const int x0 = S.i0[0][jx], rx = S.r[0][jx], y0 = S.i0[1][jy], ry = S.r[1][jy];
+      if (s == 0 || !shared_geom) {
+        const int x0 = S.i0[0][jx], rx = S.r[0][jx], y0 = S.i0[1][jy], ry = S.r[1][jy];
+#pragma unroll
+        for (int k = 0; k < SFE_SLOTS; ++k) {
+          const int i = lane + 32 * k;
+          const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+          const bool valid = (k < SFE_SLOTS - 1 || i < SFE_PLEN) && pr >= ry && pc >= rx;
+          const int X = x0 + pc, Y = y0 + pr;
+          const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
+          int Xq = X;
+          if (!xin && !yin && Y < 0 && X >= im.w - 1 && im.w >= 2) Xq = im.w - 2;  // OpenCV top-right quirk
+          // the tile spans [ox, ox+15] x [oy, oy+15], already replicate-clamped; +1 / +TS stay inside
+          toff[k] = valid ? clampi(Y - oy, 0, 14) * TS + clampi(Xq - ox, 0, 14) : 16 * TS;
+          mx[k] = xin ? 0xffffffffu : 0u;
+          mv[k] = (yin || !xin) ? 0xffffffffu : 0u;
+        }
+      }
+      const unsigned ax = __float_as_uint(S.a[0][jx]), ax1 = __float_as_uint(S.a1[0][jx]);
+      const unsigned ay = __float_as_uint(S.a[1][jy]), ay1 = __float_as_uint(S.a1[1][jy]);
+      const float axf = __uint_as_float(ax), ayf = __uint_as_float(ay);
+      const unsigned one = 0x3f800000u;
       float v[SFE_SLOTS];
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
-        const int i = lane + 32 * k;
-        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-        float r = 0.f;
-        if (i < SFE_PLEN && pr >= ry && pc >= rx) r = sample_general(f, x0 + pc, y0 + pr, im.w, im.h, ax, ax1, ay, ay1);
-        v[k] = r;
+        const float* t = S.tile + toff[k];
+        const unsigned r00 = __float_as_uint(t[0]), r01 = __float_as_uint(t[1]);
+        const unsigned r10 = __float_as_uint(t[TS]), r11 = __float_as_uint(t[TS + 1]);
+        const float t00 = __uint_as_float(r00), t01 = __uint_as_float(r01 & mx[k]);
+        const float t10 = __uint_as_float(r10 & mv[k]), t11 = __uint_as_float(r11 & mx[k] & mv[k]);
+        const float A1 = __uint_as_float((ax1 & mx[k]) | (one & ~mx[k])), B1 = __uint_as_float((ay1 & mv[k]) | (one & ~mv[k]));
+        v[k] = fmaf(t11, axf * ayf, fmaf(t10, A1 * ayf, fmaf(t01, axf * B1, t00 * (A1 * B1))));
       }
       float part = 0.f;
       if (MODE == MODE_HESSIAN) {
         float m, q;
         patch_stats(v, m, q);
+        if (is_tmpl) {
+#pragma unroll
+          for (int k = 0; k < SFE_SLOTS; ++k) T[k] = v[k];
+          tmean = m;
+          tsumsq = q;
+          return 0.f;
+        }
         const float alpha = sqrtf(tsumsq / q);
         const float beta = tmean - alpha * m;
 #pragma unroll
@@ -239,6 +294,11 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
           part = (T[k] == 0.f || v[k] == 0.f) ? part : t;
         }
       } else {
+        if (is_tmpl) {
+#pragma unroll
+          for (int k = 0; k < SFE_SLOTS; ++k) T[k] = v[k];
+          return 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < SFE_SLOTS; ++k) {
           const float diff = T[k] - v[k];
@@ -256,20 +316,14 @@ __device__ __forceinline__ float brute_hessian(WarpScratch& S, const ImgView im,
   return __shfl_sync(SFE_FULL, sc, 0);
 }
 
-// GetPatch of the template (hessian.h:54-93 / klt.h:59-96, image plane) straight from global memory
-template <int MODE>
-__device__ __forceinline__ void template_patch(const ImgView tim, float tx, float ty, int lane, float (&T)[SFE_SLOTS],
-                                            float& tmean, float& tsumsq) {
-  PatchGeom g;
-  g.x = axis_geom(tx, MODE == MODE_HESSIAN, true);
-  g.y = axis_geom(ty, MODE == MODE_HESSIAN, false);
-  sample_patch_global(tim, g, lane_pix(lane), T);
-  patch_stats(T, tmean, tsumsq);
-}
-
 __device__ __forceinline__ void load_mask(const float* __restrict__ mask, int lane, float (&mk)[SFE_SLOTS]) {
 #pragma unroll
-  for (int k = 0; k < SFE_SLOTS; ++k) mk[k] = (lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
+  for (int k = 0; k < SFE_SLOTS; ++k) mk[k] = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
+}
+
+__device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
+  if (lane < TS + 2) S.zero[lane] = 0.f;
+  __syncwarp();
 }
 
 // GetPatches (hessian.h:175-183 / klt.h:249-256) on the template pyramid + TrackFeature
@@ -286,15 +340,21 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, 
 #pragma unroll 1
   for (int i = lv - 1; i >= 0; --i) {
     const float sc = (float)(1. / (1 << i));  // pt *= 0.5 i times (exact)
-    float T[SFE_SLOTS], tmean, tsumsq;
-    template_patch<MODE>(img_of(tp, 0, i, tframe), tx * sc, ty * sc, lane, T, tmean, tsumsq);
+    float T[SFE_SLOTS], tmean = 0.f, tsumsq = 0.f;
     const float th = (MODE == MODE_KLT && i > 0) ? thr * 50.f : thr;  // klt.h:413
-    const ImgView im = img_of(sp, 0, i, sframe);
+    const ImgView tim = img_of(tp, 0, i, tframe), sim = img_of(sp, 0, i, sframe);
+    // it == -1 extracts the template patch of this level (GetPatches); it >= 0 are the Newton steps
 #pragma unroll 1
-    for (int it = 0; it < maxit; ++it) {
-      if (px < margin || py < margin || (px + margin) > (float)im.w || (py + margin) > (float)im.h) return SFE_OUT_OF_BOUNDS;
+    for (int it = -1; it < maxit; ++it) {
+      const bool is_tmpl = it < 0;
+      if (!is_tmpl && (px < margin || py < margin || (px + margin) > (float)sim.w || (py + margin) > (float)sim.h))
+        return SFE_OUT_OF_BOUNDS;
+      ImgView im;
+      im.p = is_tmpl ? tim.p : sim.p;
+      im.w = sim.w; im.h = sim.h; im.pitch = sim.pitch;  // both pyramids have the same geometry
       float d[6];
-      brute_hessian<MODE>(S, im, T, tmean, tsumsq, mk, px, py, lane, d);
+      evaluate<MODE>(S, im, is_tmpl, T, tmean, tsumsq, mk, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, d);
+      if (is_tmpl) continue;
       ++steps;
       float dx, dy;
       newton_step(d[0], d[1], d[2], d[3], d[4], d[5], dx, dy);
@@ -322,6 +382,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, 4) track_fb_kernel(PyrView fro
   const int i = blockIdx.x * TRK_WARPS + warp;
   if (i >= a.n) return;
   WarpScratch& S = scratch[warp];
+  init_scratch(S, lane);
   float mk[SFE_SLOTS];
   load_mask(mask, lane, mk);
 
