@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz with the REAL OpenCV (cv2) through oracle/tier0_cv2.py.
+
+Run in the build container (cv2 4.13 is installed there):   python tests/golden/make_golden.py
+The fixtures pin the dependency-free C oracle (oracle/oracle.c) -- and through it the CUDA path --
+against outputs of the OpenCV primitives the reference calls (hessian.h / klt.h / brute.h):
+
+  pyramid_*.npz   cv2-built pyramids (all three flavours) of a seeded 131x97 BGR frame
+  patches.npz     cv2.getRectSubPix-based GetPatch outputs (hessian.h:54-93) at interior, edge and
+                  corner centres, incl. the top-right quirk region
+  hessian.npz     BruteHessian 7-tuples (hessian.h:147-172) from tier-0 on the golden planes
+  tracks.npz      forward/backward tracks (matcher.cpp:173-206) from tier-0 ON THE cv2 PLANES
+                  (the oracle must reproduce them bit-exactly when given the same planes)
+  hamming.npz     cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) on seeded descriptors with planted ties
+
+It also re-runs the arithmetic probes that fixed the oracle's operation order (see oracle.h) and
+prints what fraction of each cv2 primitive's output the oracle reproduces bit-for-bit.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import cv2  # noqa: E402
+
+from oracle import pyoracle as po  # noqa: E402
+from oracle import tier0_cv2 as t0  # noqa: E402
+
+synth = importlib.import_module("slam-robot_b200.synth")
+
+
+def probes():
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    g = cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY)
+    print("cvtColor RGB2GRAY   bit-exact:", np.array_equal(g, po.gray_u8(bgr)))
+    codes = np.arange(256, dtype=np.uint8).reshape(1, 256)
+    conv = t0.convert_to_via_normalize(codes)
+    print("convertTo(1/255.)   bit-exact:", np.array_equal(conv, codes.astype(np.float32) * np.float32(1 / 255.)))
+    for sigma in (1.1, 0.8, 0.6):
+        k = cv2.getGaussianKernel(5, sigma, cv2.CV_32F).ravel()
+        print("gaussian taps sigma=%.1f: %s" % (sigma, [hex(int(x.view(np.uint32))) for x in k[:3]]))
+    for (h, w) in ((96, 128), (97, 131), (15, 20)):
+        img = rng.random((h, w), dtype=np.float32)
+        for sigma in (1.1, 0.8, 0.6):
+            a, b = po.gauss5(img, sigma), cv2.GaussianBlur(img, (5, 5), sigma, sigmaY=sigma)
+            main = w & ~7
+            print("GaussianBlur %.1f %dx%d: exact on cols<%d: %s, overall %.4f, max |d| %.2g" % (
+                sigma, w, h, main, np.array_equal(a[:, :main], b[:, :main]), (a == b).mean(), np.abs(a - b).max()))
+        a, b = po.pyrdown(img), cv2.pyrDown(img)
+        print("pyrDown %dx%d: exact interior cols: %s, overall %.4f, max |d| %.2g" % (
+            w, h, np.array_equal(a[:, 1:-4], b[:, 1:-4]), (a == b).mean(), np.abs(a - b).max()))
+        gx, gy = po.scharr(img)
+        cx = cv2.Sobel(img, cv2.CV_32F, 1, 0, ksize=cv2.FILTER_SCHARR, scale=1 / 32.)
+        cy = cv2.Sobel(img, cv2.CV_32F, 0, 1, ksize=cv2.FILTER_SCHARR, scale=1 / 32.)
+        main = w & ~7
+        print("Scharr %dx%d: exact on cols<%d: %s %s" % (w, h, main, np.array_equal(gx[:, :main], cx[:, :main]),
+                                                          np.array_equal(gy[:, :main], cy[:, :main])))
+    img = rng.random((48, 64), dtype=np.float32) + np.float32(0.1)
+    bad = 0
+    for _ in range(3000):
+        n, m = int(rng.integers(6, 14)), int(rng.integers(6, 14))
+        cx, cy = float(np.float32(rng.uniform(-3, 67))), float(np.float32(rng.uniform(-3, 51)))
+        bad += not np.array_equal(cv2.getRectSubPix(img, (n, m), (cx, cy)), po.rect_subpix(img, n, m, cx, cy))
+    print("getRectSubPix: %d of 3000 random windows (incl. all borders/corners) differ" % bad)
+
+
+def main():
+    probes()
+    H, W = 97, 131
+    A, B = synth.make_pairs(42, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    # pyramids from real OpenCV
+    hes_a, hes_b = t0.pyramid_hessian(A, 4), t0.pyramid_hessian(B, 4)
+    klt_a = t0.pyramid_klt(A, 3)
+    bru_a = t0.pyramid_brute(A, 3)
+    np.savez_compressed(os.path.join(HERE, "pyramid.npz"), A=A, B=B,
+                        **{"hes_a%d" % i: p for i, p in enumerate(hes_a)}, **{"hes_b%d" % i: p for i, p in enumerate(hes_b)},
+                        **{"klt_a%d_%d" % (i, k): p[k] for i, p in enumerate(klt_a) for k in range(3)},
+                        **{"bru_a%d" % i: p for i, p in enumerate(bru_a)})
+    # patches (hessian.h GetPatch through cv2.getRectSubPix)
+    rng = np.random.default_rng(7)
+    cent, lev, pat, mean, sumsq = [], [], [], [], []
+    for level in range(4):
+        h, w = hes_a[level].shape
+        pts = np.stack([rng.uniform(0.02, w - 0.02, 60), rng.uniform(0.02, h - 0.02, 60)], 1).astype(np.float32)
+        pts[:8] = [[0.5, 0.5], [w - 0.5, 0.5], [0.5, h - 0.5], [w - 0.5, h - 0.5], [w - 3.3, 0.2], [w - 6.9, 5.7], [6.4, 6.4], [6.6, 6.6]]
+        for (x, y) in pts:
+            d, m, q = t0.hes_get_patch(hes_a[level], x, y)
+            cent.append((x, y)); lev.append(level); pat.append(d); mean.append(m); sumsq.append(q)
+    np.savez_compressed(os.path.join(HERE, "patches.npz"), xy=np.float32(cent), level=np.int32(lev), patch=np.float32(pat),
+                        mean=np.float32(mean), sumsq=np.float32(sumsq))
+    # BruteHessian tuples
+    pts = synth.make_features(3, 40, H, W, margin=10, border_frac=0.3)
+    tup = []
+    for (x, y) in pts:
+        d, m, q = t0.hes_get_patch(hes_a[0], x, y)
+        s0, d6 = t0.hes_brute_hessian(hes_b[0], d, m, q, np.float32(x + 0.7), np.float32(y - 0.4))
+        tup.append([s0] + list(d6))
+    np.savez_compressed(os.path.join(HERE, "hessian.npz"), xy=pts, out7=np.float32(tup))
+    # end-to-end forward/backward tracks on the cv2 planes
+    pts = synth.make_features(5, 80, H, W, margin=8, border_frac=0.25)
+    r3 = t0.hes_track_fb(hes_a, hes_b, pts, pts, 3)
+    r4 = t0.hes_track_fb(hes_a, hes_b, pts, pts, 4)
+    np.savez_compressed(os.path.join(HERE, "tracks.npz"), xy=pts,
+                        **{"l3_" + k: np.asarray(v) for k, v in r3.items()}, **{"l4_" + k: np.asarray(v) for k, v in r4.items()})
+    print("tracks: accepted %d/80 (3 levels), %d/80 (4 levels)" % (r3["accepted"].sum(), r4["accepted"].sum()))
+    # Hamming knn with planted ties
+    t = synth.make_descriptors(1, 700, dup_frac=0.1)
+    q = synth.make_descriptors(2, 500, dup_frac=0.4, source=t)
+    idx, dist = t0.hamming_knn2_cv2(q.view(np.uint8), t.view(np.uint8))
+    print("hamming: %d queries with tied best distance" % int((dist[:, 0] == dist[:, 1]).sum()))
+    np.savez_compressed(os.path.join(HERE, "hamming.npz"), q=q, t=t, idx=idx, dist=dist)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print("%-14s %7.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,276 @@
+"""CPU-side tests (no GPU): the oracle against the committed cv2 golden vectors (and against a live
+cv2 when importable), the C ABI surface of libslamfe.so, the no-CPU-fallback rule, and host logic."""
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bits_equal
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def ulps(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+# ------------------------------------------------------------------ oracle vs golden (cv2-generated)
+
+def test_mask_properties(po):
+    m = po.mask13()
+    assert m.shape == (169,) and abs(float(m.astype(np.float64).sum()) - 169.0) < 1e-3
+    m2 = m.reshape(13, 13)
+    assert m2.argmax() in (6 * 13 + 6, 6 * 13 + 7, 7 * 13 + 6, 7 * 13 + 7)  # centre is at 6.5 (hessian.h:15-16)
+    assert np.array_equal(m2, m2.T)
+
+
+def test_pyramid_hessian_vs_cv2_golden(po):
+    g = gold("pyramid.npz")
+    for key, frame in (("hes_a", g["A"]), ("hes_b", g["B"])):
+        p = po.Pyramid(frame, 4, po.FLAVOR_HESSIAN)
+        for l in range(4):
+            ref, got = g["%s%d" % (key, l)], p.plane(l)
+            assert got.shape == ref.shape
+            assert ulps(got, ref).max() <= 2, "level %d" % l
+            if l == 0:  # level 0: exact wherever OpenCV's 8-wide SIMD body ran
+                main = ref.shape[1] & ~7
+                assert_bits_equal(got[:, :main], ref[:, :main], "L0 SIMD columns")
+            assert (got == ref).mean() > (0.9 if l < 2 else 0.7)  # tail columns weigh more on tiny levels
+
+
+def test_pyramid_klt_and_brute_vs_cv2_golden(po):
+    g = gold("pyramid.npz")
+    pk = po.Pyramid(g["A"], 3, po.FLAVOR_KLT)
+    for l in range(3):
+        for k in range(3):
+            ref, got = g["klt_a%d_%d" % (l, k)], pk.plane(l, k)
+            d = np.abs(got - ref).max()
+            assert d <= 2.5e-7, (l, k, d)  # <= 2 ulp of values in [-1, 1]
+            assert (got == ref).mean() > (0.9 if l < 2 else 0.7)
+    pb = po.Pyramid(g["A"], 3, po.FLAVOR_BRUTE)
+    assert_bits_equal(pb.plane(0), g["bru_a0"], "brute L0 (gray/255)")
+    for l in (1, 2):
+        assert ulps(pb.plane(l), g["bru_a%d" % l]).max() <= 2
+
+
+def golden_pyr(po, key, depth):
+    g = gold("pyramid.npz")
+    return po.Pyramid.from_planes([g["%s%d" % (key, l)] for l in range(depth)])
+
+
+def test_get_patch_bit_exact_vs_cv2_golden(po):
+    g = gold("patches.npz")
+    p = golden_pyr(po, "hes_a", 4)
+    for i in range(len(g["xy"])):
+        d, m, q = po.hes_get_patch(p, int(g["level"][i]), g["xy"][i, 0], g["xy"][i, 1])
+        assert_bits_equal(d, g["patch"][i], "patch %d at %s level %d" % (i, g["xy"][i], g["level"][i]))
+        # statistics use the declared lane/tree order; tier-0 emulates fmaf through float64 (exact)
+        assert_bits_equal(np.float32([m, q]), np.float32([g["mean"][i], g["sumsq"][i]]), "stats %d" % i)
+
+
+def test_brute_hessian_bit_exact_vs_golden(po):
+    g = gold("hessian.npz")
+    pa, pb = golden_pyr(po, "hes_a", 4), golden_pyr(po, "hes_b", 4)
+    for i, (x, y) in enumerate(g["xy"]):
+        d, m, q = po.hes_get_patch(pa, 0, x, y)
+        s0, d6 = po.hes_brute_hessian(pb, 0, d, m, q, np.float32(x + 0.7), np.float32(y - 0.4))
+        assert_bits_equal(np.concatenate([[s0], d6]).astype(np.float32), g["out7"][i], "BruteHessian %d" % i)
+
+
+@pytest.mark.parametrize("levels", [3, 4])
+def test_tracks_bit_exact_on_cv2_planes(po, levels):
+    """matcher.cpp:173-206 end to end: tier-0 (cv2.getRectSubPix + NumPy) and the C oracle agree bit for
+    bit when they track on the same (cv2-built) planes."""
+    g = gold("tracks.npz")
+    pa, pb = golden_pyr(po, "hes_a", 4), golden_pyr(po, "hes_b", 4)
+    r = po.hes_track_fb(pa, pb, g["xy"], g["xy"], levels)
+    pre = "l%d_" % levels
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(r[k], g[pre + k]), k
+    assert_bits_equal(r["to_xy"], g[pre + "to_xy"], "to_xy")
+    assert_bits_equal(r["back_xy"], g[pre + "back_xy"], "back_xy")
+    assert r["newton_steps"] == int(g[pre + "newton_steps"])
+    assert r["accepted"].sum() >= 60
+
+
+def test_tracks_own_pyramid_close_to_cv2_pipeline(po):
+    """Whole pipeline (oracle pyramid, <=2 ulp from cv2's in SIMD-tail columns) against the whole cv2
+    pipeline: identical flags / <=1e-3 px except for noise-sensitive features, which
+    must stay rare and are reported, not hidden."""
+    g, gp = gold("tracks.npz"), gold("pyramid.npz")
+    pa, pb = po.Pyramid(gp["A"], 4), po.Pyramid(gp["B"], 4)
+    r = po.hes_track_fb(pa, pb, g["xy"], g["xy"], 3)
+    same_flag = r["accepted"] == g["l3_accepted"]
+    close = np.linalg.norm(r["to_xy"] - g["l3_to_xy"], axis=1) <= 1e-3
+    sensitive = np.flatnonzero(~(same_flag & close))
+    print("noise-sensitive features:", sensitive.tolist())
+    assert len(sensitive) <= 0.05 * len(same_flag)
+
+
+def test_hamming_vs_cv2_bfmatcher_golden(po):
+    g = gold("hamming.npz")
+    idx, dist, ok = po.hamming256_top2(g["q"], g["t"], 4, 5, 64)
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+    assert (dist[:, 0] == dist[:, 1]).sum() > 50  # the tie rule is exercised
+    exp_ok = (dist[:, 0] <= 64) & (dist[:, 0].astype(np.int64) * 5 < dist[:, 1].astype(np.int64) * 4)
+    assert np.array_equal(ok.astype(bool), exp_ok)
+
+
+def test_hamming_edge_cases(po):
+    q = np.zeros((3, 8), np.uint32)
+    idx, dist, ok = po.hamming256_top2(q, np.zeros((0, 8), np.uint32))
+    assert (idx == -1).all() and (dist == 257).all() and not ok.any()
+    t = np.zeros((1, 8), np.uint32)
+    t[0, 3] = 0xFF
+    idx, dist, ok = po.hamming256_top2(q, t, 4, 5, 256)
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all() and (dist[:, 0] == 8).all() and ok.all()
+    full = np.full((2, 8), 0xFFFFFFFF, np.uint32)
+    _, dist, _ = po.hamming256_top2(q, full)
+    assert (dist == 256).all()
+
+
+# ------------------------------------------------------------------ live cv2 (when importable)
+
+def test_oracle_vs_live_cv2(po):
+    t0 = importlib.import_module("oracle.tier0_cv2")
+    if not t0.have_cv2():
+        pytest.skip("cv2 not importable")
+    import cv2
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (64, 96, 3), dtype=np.uint8)
+    assert np.array_equal(po.gray_u8(bgr), cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY))
+    img = rng.random((64, 96), dtype=np.float32)
+    for sigma in (1.1, 0.8, 0.6):
+        assert_bits_equal(po.gauss5(img, sigma), cv2.GaussianBlur(img, (5, 5), sigma, sigmaY=sigma), "blur %.1f" % sigma)
+    assert_bits_equal(po.pyrdown(img)[:, 1:-4], cv2.pyrDown(img)[:, 1:-4], "pyrDown interior")
+    for _ in range(300):
+        n, m = int(rng.integers(6, 14)), int(rng.integers(6, 14))
+        cx, cy = float(np.float32(rng.uniform(-3, 99))), float(np.float32(rng.uniform(-3, 67)))
+        assert_bits_equal(po.rect_subpix(img, n, m, cx, cy), cv2.getRectSubPix(img, (n, m), (cx, cy)), "subpix")
+    q = rng.integers(0, 2 ** 32, (200, 8), dtype=np.uint64).astype(np.uint32)
+    t = rng.integers(0, 2 ** 32, (300, 8), dtype=np.uint64).astype(np.uint32)
+    ci, cd = t0.hamming_knn2_cv2(q.view(np.uint8), t.view(np.uint8))
+    oi, od, _ = po.hamming256_top2(q, t)
+    assert np.array_equal(ci, oi) and np.array_equal(cd, od)
+
+
+# ------------------------------------------------------------------ KLT / brute restatements: properties
+
+def test_klt_and_brute_oracle_properties(po, synth):
+    H, W = 120, 160
+    A, B = synth.make_pairs(8, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    pts = synth.make_features(2, 40, H, W, margin=20)
+    ka, kb = po.Pyramid(A, 3, po.FLAVOR_KLT), po.Pyramid(B, 3, po.FLAVOR_KLT)
+    r = po.klt_track_fb(ka, kb, pts, pts)
+    truth = synth.true_motion(pts, H, W, 0.004, (1.7, -2.3))
+    ok = r["accepted"] == 1
+    assert ok.sum() >= 20 and np.median(np.linalg.norm(r["to_xy"] - truth, axis=1)[ok]) < 0.2
+    # identical frames: the symmetric-KLT system has A == B == C, RS == VW == 0 and d == 0
+    s = po.klt_system(ka, pts[0, 0], pts[0, 1], ka, 0, pts[0, 0], pts[0, 1])
+    assert np.allclose(s[0:4], s[4:8], rtol=1e-6) and np.allclose(s[0:4], s[8:12], rtol=1e-6)
+    assert np.abs(s[12:16]).max() < 1e-6 and np.abs(s[22:24]).max() < 1e-4
+    ba, bb = po.Pyramid(A, 3, po.FLAVOR_BRUTE), po.Pyramid(B, 3, po.FLAVOR_BRUTE)
+    rb = po.brute_track(ba, bb, pts, pts)
+    okb = rb["status"] == 0
+    assert okb.sum() >= 36 and np.median(np.linalg.norm(rb["to_xy"] - truth, axis=1)[okb]) < 0.2
+    # float loop counters (brute.h:105-106): `x += res` accumulates rounding, e.g. (0.2, 0.025) visits 16
+    # offsets per axis, not 17
+    def count(window, res):
+        x, n = np.float32(-window), 0
+        while x <= np.float32(window):
+            n += 1
+            x = np.float32(x + np.float32(res))
+        return n * n
+    coarse = sum(count(w, r) for w, r in po.BRUTE_COARSE.reshape(-1, 2))
+    fine = sum(count(w, r) for w, r in po.BRUTE_FINE.reshape(-1, 2))
+    assert count(0.2, 0.025) == 256
+    assert rb["positions"] == okb.sum() * (2 * coarse + fine)
+
+
+# ------------------------------------------------------------------ the C ABI surface
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "slamfe.h")).read()
+    return sorted(set(re.findall(r"\b(sfe_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(sfe):
+    assert declared_symbols() == sorted(sfe.EXPORTS)
+
+
+def test_library_builds_and_exports_every_symbol(sfe):
+    path = sfe.build()
+    L = ctypes.CDLL(path)
+    for s in declared_symbols():
+        assert hasattr(L, s), "libslamfe.so does not export %s" % s
+    out = subprocess.run(["cuobjdump", "-lelf", path], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out, "library must carry sm_100a code"
+
+
+def test_no_cpu_fallback(sfe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sfe.SlamFEError):
+        sfe.FrontEnd(0)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "slam-robot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "tier0_cv2" not in txt, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+
+
+def test_every_header_entry_cites_the_reference():
+    txt = open(os.path.join(ROOT, "include", "slamfe.h")).read()
+    for ref in ("matcher.cpp:173-206", "hessian.h:95-126", "hessian.h:54-93", "hessian.h:147-172", "klt.h:258-424",
+                "brute.h:129-164", "hessian.h:48-52", "matcher.cpp:304"):
+        assert ref in txt, ref
+
+
+# ------------------------------------------------------------------ host logic
+
+def test_synth_is_seeded(synth):
+    a1, b1 = synth.make_pairs(3, 2, 48, 64)
+    a2, b2 = synth.make_pairs(3, 2, 48, 64)
+    assert np.array_equal(a1.numpy(), a2.numpy()) and np.array_equal(b1.numpy(), b2.numpy())
+    assert not np.array_equal(a1.numpy(), b1.numpy())
+    p = synth.make_features(1, 100, 48, 64, margin=8, border_frac=0.2)
+    assert p.shape == (100, 2) and p.min() > 0 and (p[:, 0] < 64).all() and (p[:, 1] < 48).all()
+    d = synth.make_descriptors(1, 50, dup_frac=0.2)
+    assert d.shape == (50, 8) and d.dtype == np.uint32
+
+
+def test_shard_ranges(sfe):
+    dist = importlib.import_module("slam-robot_b200.dist")
+    for n in (0, 1, 7, 65536, 1000003):
+        for world in (1, 2, 3, 8):
+            r = [dist.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1 and sizes == dist.shard_counts(n, world)
+
+
+def test_bench_reference_arm_runs():
+    """bench.py --impl reference prints one JSON line with the contract's keys (tiny sample)."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-pairs", "1"], stdout=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frame pairs/s"
