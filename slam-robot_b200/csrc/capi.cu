@@ -15,6 +15,8 @@ struct sfe_ctx {
   cudaStream_t own_stream;
   cudaStream_t stream;
   float* d_mask;
+  int* d_counter;  // work-queue head of the persistent tracking kernels
+  int num_sms;
   float h_mask[SFE_PLEN];
   // grow-on-demand device scratch for the host-pointer entry points
   void* scratch;
@@ -187,7 +189,8 @@ int sfe_create(int device, sfe_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   build_mask(ctx->h_mask);
-  if (cudaMalloc(&ctx->d_mask, sizeof(ctx->h_mask)) != cudaSuccess ||
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMalloc(&ctx->d_counter, 256) != cudaSuccess || cudaMalloc(&ctx->d_mask, sizeof(ctx->h_mask)) != cudaSuccess ||
       cudaMemcpy(ctx->d_mask, ctx->h_mask, sizeof(ctx->h_mask), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -204,6 +207,7 @@ void sfe_destroy(sfe_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
   cudaFree(ctx->d_mask);
+  cudaFree(ctx->d_counter);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -372,7 +376,7 @@ int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sf
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, levels, default_levels, thr, maxit, fb_max,
               back_xy, status_fwd, status_bwd, accepted, steps};
-  return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, ctx->stream), "track launch: %s");
+  return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "track launch: %s");
 }
 
 
@@ -443,7 +447,7 @@ int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, cons
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, nullptr, from->view.depth, thr, maxit, fb_max,
               back_xy, status_fwd, status_bwd, accepted, steps};
-  return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, ctx->stream), "klt launch: %s");
+  return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "klt launch: %s");
 }
 
 int sfe_klt_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,

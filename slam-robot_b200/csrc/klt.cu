@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(128) klt_system_kernel(PyrView tv, int tframe,
 
 }  // namespace
 
-int launch_track_klt(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask, cudaStream_t s) {
-  return launch_track_fb<MODE_KLT>(from, to, a, mask, s);
+int launch_track_klt(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask, int* counter,
+                     int num_sms, cudaStream_t s) {
+  return launch_track_fb<MODE_KLT>(from, to, a, mask, counter, num_sms, s);
 }
 
 int launch_klt_system(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level, int n,

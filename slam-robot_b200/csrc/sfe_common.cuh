@@ -84,14 +84,14 @@ struct TrackArgs {
 int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_stride,
                      size_t frame_stride, int first, int count, cudaStream_t s);
 int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a,
-                         const float* mask, cudaStream_t s);
+                         const float* mask, int* counter, int num_sms, cudaStream_t s);
 int launch_get_patches(const PyrView& v, int frame, int level, int n, const float* xy,
                        float* patches, float* mean, float* sumsq, cudaStream_t s);
 int launch_brute_hessian(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level,
                          int n, const float* txy, const float* xy, float* out7, const float* mask,
                          cudaStream_t s);
 int launch_track_klt(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask,
-                     cudaStream_t s);
+                     int* counter, int num_sms, cudaStream_t s);
 int launch_klt_system(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level, int n,
                       const float* txy, const float* xy, float* out24, const float* mask,
                       cudaStream_t s);

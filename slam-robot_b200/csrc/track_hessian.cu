@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
 }  // namespace
 
 int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask,
-                         cudaStream_t s) {
-  return launch_track_fb<MODE_HESSIAN>(from, to, a, mask, s);
+                         int* counter, int num_sms, cudaStream_t s) {
+  return launch_track_fb<MODE_HESSIAN>(from, to, a, mask, counter, num_sms, s);
 }
 
 int launch_get_patches(const PyrView& v, int frame, int level, int n, const float* xy, float* patches,

@@ -36,6 +36,9 @@ namespace {
 enum { MODE_HESSIAN = 0, MODE_KLT = 1 };
 
 constexpr int TRK_WARPS = 4;
+#ifndef TRK_MINB
+#define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
+#endif
 constexpr int TS = 16;  // tile row stride (floats)
 
 // per-warp shared scratch
@@ -375,17 +378,24 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(32 * TRK_WARPS, 4) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
-                                                                  const float* __restrict__ mask) {
+// Persistent: the grid is sized to the machine (TRK_MINB CTAs per SM) and every warp pulls the next
+// feature from a global counter, so no warp slot idles while a CTA-mate finishes a feature that needs
+// more Newton steps (features take 8..80 steps; with static assignment a quarter of the slots idled).
+__global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
+                                                                           const float* __restrict__ mask,
+                                                                           int* __restrict__ next_feature) {
   __shared__ WarpScratch scratch[TRK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * TRK_WARPS + warp;
-  if (i >= a.n) return;
   WarpScratch& S = scratch[warp];
   init_scratch(S, lane);
   float mk[SFE_SLOTS];
   load_mask(mask, lane, mk);
-
+#pragma unroll 1
+  for (;;) {
+  int i = 0;
+  if (lane == 0) i = atomicAdd(next_feature, 1);
+  i = __shfl_sync(SFE_FULL, i, 0);
+  if (i >= a.n) break;
   const int pair = i / a.n_per_pair;
   const int ff = a.from_first + pair, tf = a.to_first + pair;
   const float fx = a.from_xy[2 * i], fy = a.from_xy[2 * i + 1];
@@ -420,14 +430,18 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, 4) track_fb_kernel(PyrView fro
     if (a.accepted) a.accepted[i] = ok ? 1 : 0;
     if (a.steps) a.steps[i] = steps;
   }
+  }
 }
 
 template <int MODE>
-int launch_track_fb(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask, cudaStream_t s) {
+int launch_track_fb(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask, int* counter,
+                    int num_sms, cudaStream_t s) {
   if (a.n <= 0) return 0;
-  int blocks = (a.n + TRK_WARPS - 1) / TRK_WARPS;
-  track_fb_kernel<MODE><<<blocks, 32 * TRK_WARPS, 0, s>>>(from, to, a, mask);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
+  if (e != cudaSuccess) return -(int)e;
+  int blocks = min((a.n + TRK_WARPS - 1) / TRK_WARPS, num_sms * TRK_MINB);
+  track_fb_kernel<MODE><<<blocks, 32 * TRK_WARPS, 0, s>>>(from, to, a, mask, counter);
+  e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -(int)e;
 }
 
