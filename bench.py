@@ -256,9 +256,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def host_threads():
+    """Host threads available to this process (torchrun exports OMP_NUM_THREADS=1: ask the scheduler instead)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_step(po, A, B, pts, q, t, fast=True, nthreads=0):
     """The same step on the host: the oracle port of the reference's CPU path, all host threads."""
     acc = 0
+    nthreads = nthreads or host_threads()
     for p in range(len(A)):
         pa = po.Pyramid(A[p], DEPTH, po.FLAVOR_HESSIAN, fast=fast)
         pb = po.Pyramid(B[p], DEPTH, po.FLAVOR_HESSIAN, fast=fast)
@@ -282,7 +291,7 @@ def cpu_baseline(sample_pairs=4):
     from oracle import pyoracle as po
     po.build(fast=True, native=True)  # -march=native for THIS host
     A, B, pts, q, t = cpu_inputs(sample_pairs)
-    cores = po.num_threads()
+    cores = host_threads()
     cpu_step(po, A[:1], B[:1], pts[:NFEAT], q[:NFEAT], t[:NFEAT])  # warm-up
     t0 = time.perf_counter()
     cpu_step(po, A, B, pts, q, t)
@@ -305,7 +314,7 @@ def run_reference(args):
     po.build(fast=True, native=True)
     pairs = args.cpu_pairs
     A, B, pts, q, t = cpu_inputs(pairs)
-    cores = po.num_threads()
+    cores = host_threads()
     for _ in range(args.warmup):
         cpu_step(po, A[:1], B[:1], pts[:NFEAT], q[:NFEAT], t[:NFEAT])
     t0 = time.perf_counter()

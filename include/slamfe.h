@@ -116,6 +116,18 @@ int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sf
                      float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                      uint8_t* accepted, int32_t* steps);
 
+/* Replaces one-directional tracker->TrackFeature(stack, GetPatches(tmpl, tmpl_pt, levels), thr, maxit, &pt)
+ * (hessian.h:175-183 + :243-264, or the klt.h equivalents for SFE_KLT pyramids) for a batch: the
+ * template patches are taken from `tmpl` at tmpl_xy, the search runs on `search` from the seed xy,
+ * which is overwritten only on success (hessian.h:262).  Pair/frame addressing as in sfe_track_fb. */
+int sfe_track(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_first, const sfe_pyr* search, int search_first,
+              int n, int n_per_pair, const float* tmpl_xy, float* xy, const int32_t* levels,
+              int default_levels, float thr, int maxit, int32_t* status, int32_t* steps);
+int sfe_track_dev(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_first, const sfe_pyr* search,
+                  int search_first, int n, int n_per_pair, const float* tmpl_xy, float* xy,
+                  const int32_t* levels, int default_levels, float thr, int maxit, int32_t* status,
+                  int32_t* steps);
+
 /* Debug/parity accessors, one call per feature list on frame `frame` of `pyr`:
  * GetPatch (hessian.h:54-93): patches [n][169], mean [n], sumsq [n]. */
 int sfe_get_patches(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int n,

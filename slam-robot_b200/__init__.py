@@ -30,7 +30,7 @@ EXPORTS = [
     "sfe_create", "sfe_destroy", "sfe_last_error", "sfe_set_stream", "sfe_sync", "sfe_get_mask", "sfe_host_alloc",
     "sfe_host_free", "sfe_launch_count", "sfe_pyr_create", "sfe_pyr_destroy", "sfe_pyr_level_size",
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
-    "sfe_track_fb_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
+    "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
 ]
 
@@ -95,6 +95,9 @@ def lib():
     trk = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp, vp, vp]
     L.sfe_track_fb.argtypes = trk
     L.sfe_track_fb_dev.argtypes = trk
+    one = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, f32, i32, vp, vp]
+    L.sfe_track.argtypes = one
+    L.sfe_track_dev.argtypes = one
     L.sfe_get_patches.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.sfe_brute_hessian.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp]
     klt = [vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, f32, vp, vp, vp, vp, vp]
@@ -236,6 +239,21 @@ class FrontEnd:
         o = dict(o)
         o["to_xy"] = to_xy
         return o
+
+    def track(self, ptmpl, psearch, tmpl_xy, seed_xy, levels=3, thr=0.001, maxit=10, n_per_pair=None, tmpl_first=0,
+              search_first=0):
+        """One-directional TrackFeature (hessian.h:243-264 / klt.h:403-424) for a batch (host path)."""
+        tmpl_xy = _np(tmpl_xy, np.float32).reshape(-1, 2)
+        n = len(tmpl_xy)
+        xy = _np(seed_xy, np.float32).reshape(-1, 2).copy()
+        lv_arr = None if np.isscalar(levels) else _np(levels, np.int32)
+        st = np.empty(n, np.int32)
+        steps = np.empty(n, np.int32)
+        npp = n if n_per_pair is None else int(n_per_pair)
+        self._chk(self.L.sfe_track(self.h, ptmpl.h, tmpl_first, psearch.h, search_first, n, max(npp, 1), _ptr(tmpl_xy),
+                                   _ptr(xy), _ptr(lv_arr), int(levels) if lv_arr is None else 3, thr, maxit, _ptr(st),
+                                   _ptr(steps)))
+        return dict(xy=xy, status=st, steps=steps)
 
     def get_patches(self, pyr, level, xy, frame=0):
         xy = _np(xy, np.float32).reshape(-1, 2)

@@ -375,7 +375,7 @@ int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sf
     return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_track_fb needs SFE_HESSIAN pyramids");
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, levels, default_levels, thr, maxit, fb_max,
-              back_xy, status_fwd, status_bwd, accepted, steps};
+              back_xy, status_fwd, status_bwd, accepted, steps, 2};
   return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "track launch: %s");
 }
 
@@ -392,6 +392,38 @@ int sfe_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_py
                     [&](float* df, float* dt, int32_t* dl, float* db, int32_t* s1, int32_t* s2, uint8_t* acc, int32_t* st) {
                       return sfe_track_fb_dev(ctx, from, from_first, to, to_first, n, n_per_pair, df, dt, dl,
                                               default_levels, thr, maxit, fb_max, db, s1, s2, acc, st);
+                    });
+}
+
+int sfe_track_dev(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_first, const sfe_pyr* search, int search_first, int n,
+                  int n_per_pair, const float* tmpl_xy, float* xy, const int32_t* levels, int default_levels, float thr,
+                  int maxit, int32_t* status, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  int rc = check_pairs(ctx, tmpl, tmpl_first, search, search_first, n, n_per_pair);
+  if (rc || n == 0) return rc;
+  if (!tmpl_xy || !xy || default_levels < 1 || maxit < 0) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (tmpl->flavor != search->flavor || tmpl->flavor == SFE_BRUTE)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_track needs two SFE_HESSIAN or two SFE_KLT pyramids");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  TrackArgs a{n, n_per_pair, tmpl_first, search_first, tmpl_xy, xy, levels, default_levels, thr, maxit, 0.f,
+              nullptr, status, nullptr, nullptr, steps, 1};
+  int r = tmpl->flavor == SFE_HESSIAN
+              ? launch_track_hessian(tmpl->view, search->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream)
+              : launch_track_klt(tmpl->view, search->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream);
+  return launched(ctx, r, "track launch: %s");
+}
+
+int sfe_track(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_first, const sfe_pyr* search, int search_first, int n,
+              int n_per_pair, const float* tmpl_xy, float* xy, const int32_t* levels, int default_levels, float thr,
+              int maxit, int32_t* status, int32_t* steps) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (n == 0) return SFE_SUCCESS;
+  if (n < 0 || !tmpl_xy || !xy) return fail(ctx, SFE_ERR_INVALID, "%s", "bad track arguments");
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return track_host(ctx, n, tmpl_xy, xy, levels, nullptr, status, nullptr, nullptr, steps,
+                    [&](float* df, float* dt, int32_t* dl, float*, int32_t* s1, int32_t*, uint8_t*, int32_t* st) {
+                      return sfe_track_dev(ctx, tmpl, tmpl_first, search, search_first, n, n_per_pair, df, dt, dl,
+                                           default_levels, thr, maxit, s1, st);
                     });
 }
 
@@ -446,7 +478,7 @@ int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, cons
     return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_klt_track_fb needs SFE_KLT pyramids");
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, nullptr, from->view.depth, thr, maxit, fb_max,
-              back_xy, status_fwd, status_bwd, accepted, steps};
+              back_xy, status_fwd, status_bwd, accepted, steps, 2};
   return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "klt launch: %s");
 }
 

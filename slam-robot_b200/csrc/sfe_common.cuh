@@ -78,6 +78,7 @@ struct TrackArgs {
   int32_t* status_bwd;
   uint8_t* accepted;
   int32_t* steps;
+  int ndir;  // 2: forward + backward (matcher.cpp:173-206); 1: forward only (TrackFeature, hessian.h:243-264)
 };
 
 // each returns the number of kernels launched (negative cudaError on failure)

@@ -406,8 +406,9 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
   float bx = fx, by = fy;  // matcher.cpp:181
   // dir 0: template from `from` at from_pt, search `to` from the seed (matcher.cpp:175-176)
   // dir 1: template from `to` at the forward result, search `from` from from_pt (matcher.cpp:180-182)
+  st[1] = SFE_OK;
 #pragma unroll 1
-  for (int dir = 0; dir < 2; ++dir) {
+  for (int dir = 0; dir < a.ndir; ++dir) {
     const PyrView& tp = dir == 0 ? from : to;
     const PyrView& sp = dir == 0 ? to : from;
     float x = dir == 0 ? tx : bx, y = dir == 0 ? ty : by;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
     if (dir == 0) { tx = x; ty = y; st[0] = s; } else { bx = x; by = y; st[1] = s; }
   }
   bool ok = !(st[0] || st[1]);  // matcher.cpp:192
-  if (ok) {
+  if (ok && a.ndir == 2) {
     float ddx = fx - bx, ddy = fy - by;
     double nrm = sqrt(__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)));
     if (nrm > (double)a.fb_max) ok = false;  // matcher.cpp:201
