@@ -15,7 +15,8 @@ def test_mask_matches_oracle(fe, po):
     assert_bits_equal(fe.mask(), po.mask13(), "mask (hessian.h:11-30)")
 
 
-@pytest.mark.parametrize("shape,depth", [((480, 640), 6), ((97, 131), 5), ((270, 481), 8), ((33, 47), 3)])
+@pytest.mark.parametrize("shape,depth", [((480, 640), 6), ((97, 131), 5), ((270, 481), 8), ((33, 47), 3), ((100, 200), 5),
+                                         ((64, 72), 4), ((250, 1000), 6)])
 @pytest.mark.parametrize("flavor", [0, 1, 2])
 def test_pyramid_bit_exact(fe, po, synth, shape, depth, flavor):
     H, W = shape
@@ -26,6 +27,20 @@ def test_pyramid_bit_exact(fe, po, synth, shape, depth, flavor):
         for l in range(depth):
             for plane in range(3 if flavor == 1 else 1):
                 assert_bits_equal(gp.plane(l, f, plane), op.plane(l, plane), "flavor %d frame %d level %d plane %d" % (flavor, f, l, plane))
+
+
+def test_pyramid_1080p_8_levels_bit_exact(fe, po, synth):
+    """BASELINE config 3 geometry: 1920x1080, 8 levels (1920 ... 15x9), with a strided host buffer."""
+    H, W = 1080, 1920
+    frame = synth.make_frames(3, 1, H, W).numpy()[0]
+    padded = np.zeros((H, W * 3 + 64), np.uint8)
+    padded[:, :W * 3] = frame.reshape(H, W * 3)
+    gp = fe.pyramid(W, H, 8, 0, 1)
+    rc = fe.L.sfe_pyr_build(fe.h, gp.h, padded.ctypes.data, padded.strides[0], padded.strides[0] * H, 0, 1)
+    assert rc == 0
+    op = po.Pyramid(frame, 8)
+    for l in range(8):
+        assert_bits_equal(gp.plane(l), op.plane(l), "1080p level %d" % l)
 
 
 def _features(synth, n, H, W, seed=5, border=0.2):
