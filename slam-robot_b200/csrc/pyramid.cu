@@ -12,6 +12,8 @@
 //   pyr_down_kernel  pyrDown and the following 5x5 blur fused: the (2T+11)^2 footprint of the
 //                    previous level is staged once in shared memory, both separable passes of both
 //                    filters run out of shared memory, the level is written once.
+#include <stdlib.h>
+
 #include "sfe_common.cuh"
 
 namespace {
@@ -290,13 +292,16 @@ __global__ void __launch_bounds__(F_THREADS) pyr_l0_hessian_fast(PyrView v, cons
   }
 }
 
-// pyrDown + 5x5 blur, 64x32 outputs per CTA.
-constexpr int D_TW = 64, D_TH = 32, D_THREADS = 256;
-constexpr int D_PDW = D_TW + 8;        // pyrDown tile: columns x0-4 .. x0+TW+3 (blur halo 2, padded to 4)
-constexpr int D_PDH = D_TH + 4;        // rows y0-2 .. y0+TH+1
-constexpr int D_PW = 2 * D_PDW + 8;    // previous-level tile: columns 2*x0-12 .. 2*x0+139 (152)
-constexpr int D_PH = 2 * D_PDH + 3;    // rows 2*y0-6 .. 2*y0+68 (75)
-constexpr size_t D_SMEM = sizeof(float) * ((size_t)D_PH * D_PW + (size_t)D_PH * D_PDW);
+// pyrDown + 5x5 blur, TW x TH outputs per CTA (64x32 for the big levels, 32x16 for the small ones).
+constexpr int D_THREADS = 256;
+template <int TW, int TH>
+struct DownTile {
+  static constexpr int PDW = TW + 8;      // pyrDown tile: columns x0-4 .. x0+TW+3 (blur halo 2, padded to 4)
+  static constexpr int PDH = TH + 4;      // rows y0-2 .. y0+TH+1
+  static constexpr int PW = 2 * PDW + 8;  // previous-level tile: columns 2*x0-12 .. (152 for TW = 64)
+  static constexpr int PH = 2 * PDH + 3;  // rows 2*y0-6 .. (75 for TH = 32)
+  static constexpr size_t SMEM = sizeof(float) * ((size_t)PH * PW + (size_t)PH * PDW);
+};
 
 __device__ __forceinline__ float pd_h(float m2, float m1, float c, float p1, float p2) {
   return ((m2 + p2) + (m1 + p1) * 4.f) + c * 6.f;
@@ -305,10 +310,13 @@ __device__ __forceinline__ float pd_v(float r0, float r1, float r2, float r3, fl
   return (((r1 + r3) + r2) * 4.f + ((r0 + r4) + (r2 + r2))) * (1.f / 256.f);
 }
 
+template <int D_TW, int D_TH>
 __global__ void __launch_bounds__(D_THREADS) pyr_down_blur_fast(const float* __restrict__ prev_base, long long prev_fs,
                                                                 int pw, int ph, int ppitch, float* __restrict__ cur_base,
                                                                 long long cur_fs, int cw, int ch, int cpitch, int first,
                                                                 int blur_id) {
+  constexpr int D_PDW = DownTile<D_TW, D_TH>::PDW, D_PDH = DownTile<D_TW, D_TH>::PDH;
+  constexpr int D_PW = DownTile<D_TW, D_TH>::PW, D_PH = DownTile<D_TW, D_TH>::PH;
   extern __shared__ __align__(16) float smem[];
   float (*P)[D_PW] = reinterpret_cast<float (*)[D_PW]>(smem);                  // [D_PH][D_PW]
   float (*Hh)[D_PDW] = reinterpret_cast<float (*)[D_PDW]>(smem + D_PH * D_PW);  // [D_PH][D_PDW]
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(D_THREADS) pyr_down_blur_fast(const float* __r
   const Taps t = taps_for(blur_id);
   const bool xedge = x0 < 2 || x0 + D_TW + 2 > cw, yedge = y0 < 2 || y0 + D_TH + 2 > ch;
   for (int it = tid; it < D_PDH * (D_TW / 4); it += D_THREADS) {
-    const int i = it >> 4, j4 = it & 15;
+    const int i = it / (D_TW / 4), j4 = it - i * (D_TW / 4);
     float4 o;
     if (!xedge) {
       const float2 a = *reinterpret_cast<const float2*>(&D[i][4 * j4 + 2]);
@@ -403,43 +411,48 @@ __global__ void __launch_bounds__(D_THREADS) pyr_down_blur_fast(const float* __r
   }
   __syncthreads();
   // ---- blur: columns.  B row index of image row y is y - y0 + 2.
-  {
-    const int cg = tid & 15, seg = tid >> 4;  // 16 column groups x 16 row pairs
-    const int x = x0 + 4 * cg;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int y = y0 + 2 * seg + k;
-      if (y < ch && x < cw) {
-        int i0, i1, i2, i3, i4;
-        if (!yedge) { i0 = 2 * seg + k; i1 = i0 + 1; i2 = i0 + 2; i3 = i0 + 3; i4 = i0 + 4; }
-        else {
-          i0 = reflect101(y - 2, ch) - y0 + 2; i1 = reflect101(y - 1, ch) - y0 + 2; i2 = y - y0 + 2;
-          i3 = reflect101(y + 1, ch) - y0 + 2; i4 = reflect101(y + 2, ch) - y0 + 2;
-        }
-        const float4 r0 = *reinterpret_cast<const float4*>(&B[i0][4 * cg]), r1 = *reinterpret_cast<const float4*>(&B[i1][4 * cg]);
-        const float4 r2 = *reinterpret_cast<const float4*>(&B[i2][4 * cg]), r3 = *reinterpret_cast<const float4*>(&B[i3][4 * cg]);
-        const float4 r4 = *reinterpret_cast<const float4*>(&B[i4][4 * cg]);
-        float4 o;
-        o.x = blur_col(r0.x, r1.x, r2.x, r3.x, r4.x, t);
-        o.y = blur_col(r0.y, r1.y, r2.y, r3.y, r4.y, t);
-        o.z = blur_col(r0.z, r1.z, r2.z, r3.z, r4.z, t);
-        o.w = blur_col(r0.w, r1.w, r2.w, r3.w, r4.w, t);
-        *reinterpret_cast<float4*>(cur + (size_t)y * cpitch + x) = o;  // cw % 4 == 0
+  for (int it = tid; it < D_TH * (D_TW / 4); it += D_THREADS) {
+    const int r = it / (D_TW / 4), cg = it - r * (D_TW / 4);
+    const int x = x0 + 4 * cg, y = y0 + r;
+    if (y < ch && x < cw) {
+      int i0, i1, i2, i3, i4;
+      if (!yedge) { i0 = r; i1 = r + 1; i2 = r + 2; i3 = r + 3; i4 = r + 4; }
+      else {
+        i0 = reflect101(y - 2, ch) - y0 + 2; i1 = reflect101(y - 1, ch) - y0 + 2; i2 = r + 2;
+        i3 = reflect101(y + 1, ch) - y0 + 2; i4 = reflect101(y + 2, ch) - y0 + 2;
       }
+      const float4 r0 = *reinterpret_cast<const float4*>(&B[i0][4 * cg]), r1 = *reinterpret_cast<const float4*>(&B[i1][4 * cg]);
+      const float4 r2 = *reinterpret_cast<const float4*>(&B[i2][4 * cg]), r3 = *reinterpret_cast<const float4*>(&B[i3][4 * cg]);
+      const float4 r4 = *reinterpret_cast<const float4*>(&B[i4][4 * cg]);
+      float4 o;
+      o.x = blur_col(r0.x, r1.x, r2.x, r3.x, r4.x, t);
+      o.y = blur_col(r0.y, r1.y, r2.y, r3.y, r4.y, t);
+      o.z = blur_col(r0.z, r1.z, r2.z, r3.z, r4.z, t);
+      o.w = blur_col(r0.w, r1.w, r2.w, r3.w, r4.w, t);
+      *reinterpret_cast<float4*>(cur + (size_t)y * cpitch + x) = o;  // cw % 4 == 0
     }
   }
 }
 
 }  // namespace
 
-int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_stride,
-                     size_t frame_stride, int first, int count, cudaStream_t s) {
-  int launches = 0;
+namespace {
+template <int TW, int TH>
+void launch_down_fast(const PyrView& v, int l, int first, int count, int blur_id, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pyr_down_blur_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM);
+    cudaFuncSetAttribute(pyr_down_blur_fast<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DownTile<TW, TH>::SMEM);
     attr_set = true;
   }
+  dim3 gf((v.w[l] + TW - 1) / TW, (v.h[l] + TH - 1) / TH, count);
+  pyr_down_blur_fast<TW, TH><<<gf, D_THREADS, DownTile<TW, TH>::SMEM, s>>>(
+      v.base[0][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1], v.pitch[l - 1], v.base[0][l], v.frame_stride[l],
+      v.w[l], v.h[l], v.pitch[l], first, blur_id);
+}
+
+int build_chunk(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first,
+                int count, cudaStream_t s) {
+  int launches = 0;
   dim3 g0((v.w[0] + L0_TW - 1) / L0_TW, (v.h[0] + L0_TH - 1) / L0_TH, count);
   const bool fast_l0 = flavor == SFE_HESSIAN && v.w[0] % 4 == 0 && ((uintptr_t)bgr & 3) == 0 && row_stride % 4 == 0 &&
                        frame_stride % 4 == 0;
@@ -455,15 +468,12 @@ int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t ro
     int blur_id = flavor == SFE_HESSIAN ? 1 : (flavor == SFE_KLT ? 2 : -1);
     // fast path: blurred plane, both levels 4-float aligned, level at least one blur reach wide/high
     const bool fast_dn = blur_id >= 0 && v.w[l] % 4 == 0 && v.w[l - 1] % 4 == 0 && v.w[l] >= 8 && v.h[l] >= 8;
-    if (fast_dn) {
-      dim3 gf((v.w[l] + D_TW - 1) / D_TW, (v.h[l] + D_TH - 1) / D_TH, count);
-      pyr_down_blur_fast<<<gf, D_THREADS, D_SMEM, s>>>(v.base[0][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1],
-                                                       v.pitch[l - 1], v.base[0][l], v.frame_stride[l], v.w[l], v.h[l],
-                                                       v.pitch[l], first, blur_id);
-    } else
-    pyr_down_kernel<<<g, DN_THREADS, 0, s>>>(v.base[0][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1],
-                                             v.pitch[l - 1], v.base[0][l], v.frame_stride[l], v.w[l], v.h[l],
-                                             v.pitch[l], first, blur_id, 1.f);
+    if (fast_dn && v.w[l] >= 256) launch_down_fast<64, 32>(v, l, first, count, blur_id, s);
+    else if (fast_dn) launch_down_fast<32, 16>(v, l, first, count, blur_id, s);
+    else
+      pyr_down_kernel<<<g, DN_THREADS, 0, s>>>(v.base[0][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1],
+                                               v.pitch[l - 1], v.base[0][l], v.frame_stride[l], v.w[l], v.h[l],
+                                               v.pitch[l], first, blur_id, 1.f);
     ++launches;
     if (flavor == SFE_KLT) {
       for (int p = 1; p <= 2; ++p) {  // klt.h:123-124
@@ -473,6 +483,29 @@ int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t ro
         ++launches;
       }
     }
+  }
+  return launches;
+}
+}  // namespace
+
+// Optional chunking of the frame batch (SFE_PYR_CHUNK_MB of level-0 planes per chunk) so that a chunk's
+// level-l planes are still in L2 when level l+1 reads them.  Measured on B200 it does not pay -- the
+// kernels are issue-bound, not L2-bound, and every extra launch adds a tail -- so the default is one
+// chunk; the knob stays for experiments (profiles/README.md).
+int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_stride,
+                     size_t frame_stride, int first, int count, cudaStream_t s) {
+  static int chunk_mb = -1;
+  if (chunk_mb < 0) {
+    const char* e = getenv("SFE_PYR_CHUNK_MB");
+    chunk_mb = e ? atoi(e) : 1 << 20;  // measured: fewer, larger launches win (profiles/README.md)
+  }
+  const size_t l0_bytes = (size_t)v.frame_stride[0] * sizeof(float) * (flavor == SFE_KLT ? 3 : 1);
+  int chunk = (int)(((size_t)chunk_mb << 20) / (l0_bytes ? l0_bytes : 1));
+  if (chunk < 1) chunk = 1;
+  int launches = 0;
+  for (int f = 0; f < count; f += chunk) {
+    const int n = count - f < chunk ? count - f : chunk;
+    launches += build_chunk(v, flavor, bgr + (size_t)f * frame_stride, row_stride, frame_stride, first + f, n, s);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? launches : -(int)e;
