@@ -1,23 +1,436 @@
-// track_hessian.cu -- P1, the live path: HessianTracker forward/backward (track_impl.cuh,
-// MODE_HESSIAN) plus the GetPatch / BruteHessian parity accessors.
-#include "track_impl.cuh"
+// track_hessian.cu -- P1, the live path: HessianTracker (hessian.h) driven forward and backward as
+// matcher.cpp:173-206 does, plus the GetPatch / BruteHessian parity accessors.
+//
+// One warp per feature, persistent grid with a dynamic feature queue; the whole chain (template
+// patches, coarse-to-fine Newton iterations, backward track, consistency gate) runs inside one
+// launch with no host round trips.
+//
+// The hot loop is BruteHessian (hessian.h:147-172): six 13x13 bilinear patches at offsets of
+// +-0.02 px around the current point, each scored against the template.  The six patches share one
+// 16x16 footprint (origin floor(x)-7), staged once per Newton step in shared memory with replicate
+// clamping applied at load time.  Three sampling routes feed ONE common tail (patch statistics ->
+// packed warp reduction -> lane-parallel alpha/beta -> scores -> packed reduction -> lane-parallel
+// finite differences):
+//   fast      all six shifts share their integer taps, no GetPatch clipping, footprint inside the
+//             image: every lane loads the 4 taps of its <= 6 patch pixels once and evaluates six
+//             weight sets (fully unrolled, patch values stay in registers);
+//   general   image borders (cv::getRectSubPix's per-pixel 2-tap rules and its top-right
+//             irregularity), GetPatch's left/top clipping, or a shift that crosses an integer
+//             boundary: a compact runtime loop over the shifts writes the patch values to a per-warp
+//             shared scratch, from which the common tail reads them back;
+//   template  GetPatch of the template patch (one shift): a 4-tap pass straight from the tile, or
+//             one iteration of the general loop.
+// The exact-zero skip of ScorePatchMatch (hessian.h:134) is folded away where it cannot trigger:
+// template zeros become zero mask weights once per level (x*0 adds an exact zero), and candidate
+// zeros are impossible when the staged footprint is strictly positive and nothing is clipped, so
+// only footprints that contain a zero run the select variant of the score loop.
+//
+// Code size is a first-class constraint: every warp sits at a different point of a long dependent
+// chain, so the body has to stay inside the 32 KB L1.5 instruction cache (profiles/README.md).
+#include "patch.cuh"
 
 namespace {
 
+constexpr int TRK_WARPS = 4;
+#ifndef TRK_MINB
+#define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
+#endif
+constexpr int TS = 16;          // tile row stride (floats)
+constexpr int ZOFF = 16 * TS;   // taps of unused patch entries point at the zero region behind the tile
+
+struct WarpScratch {
+  float tile[16 * TS];
+  float zero[TS + 2];                // must directly follow tile
+  float pad[32 - (TS + 2) % 32];
+  float v[6 * SFE_SLOTS * 32];       // general route: patch value of shift s, slot k, lane l at [(s*6+k)*32 + l]
+};
+
+// x variants live in lanes 0..2 (p, p-h, p+h), y variants in lanes 4..6; BruteHessian's shifts
+// (0,0) (-h,0) (0,-h) (+h,0) (0,+h) (+h,+h) (hessian.h:154-161) pick variant (SXP>>2s)&3 / (SYP>>2s)&3.
+constexpr unsigned SXP = 0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 2u << 10;
+constexpr unsigned SYP = 0u | 0u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 2u << 10;
+
+// Lane-parallel geometry of one BruteHessian: lane j evaluates one axis variant.  Shifted coordinates
+// are formed in double and rounded to float (cv::Point2f(pt.x - h, pt.y), hessian.h:155-160).
+__device__ __forceinline__ AxisGeom lane_geom(float x, float y, int lane) {
+  const bool isy = lane & 4;
+  const int var = lane & 3;
+  const double off = var == 1 ? -0.02 : (var == 2 ? 0.02 : 0.0);
+  const float p = isy ? y : x;
+  const float ps = (float)((double)p + off);  // + 0.0 is exact
+  return axis_geom(ps, true, !isy);
+}
+
+// Stage the replicate-clamped 16x16 footprint; returns true when it holds a value <= 0.
+__device__ __forceinline__ bool stage_tile(WarpScratch& S, const ImgView& im, int ox, int oy, int lane) {
+  const int c = lane & 15, rsub = lane >> 4;
+  const float* colp = im.p + clampi(ox + c, 0, im.w - 1);
+  float mn = 1.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int row = clampi(oy + 2 * j + rsub, 0, im.h - 1);
+    const float val = __ldg(colp + (long long)row * im.pitch);
+    S.tile[(2 * j + rsub) * TS + c] = val;
+    mn = fminf(mn, val);
+  }
+  const bool nonpos = __any_sync(SFE_FULL, mn <= 0.f);
+  __syncwarp();
+  return nonpos;
+}
+
+// General sampling route: `nshift` shifts of the BruteHessian pattern (1 for a template patch),
+// cv::getRectSubPix's border rules per pixel.  "full" 4-tap, "vertical" 2-tap (overflow column, and
+// corners), "horizontal" 2-tap (overflow row): with the unused taps zeroed and A1' = xin ? 1-a : 1,
+// B1' = vert ? 1-b : 1 the weights (A1'B1', aB1', A1'b, ab) reproduce the rule exactly (x*1 is exact
+// and a zero tap adds an exact zero), so one FMA chain serves all pixels.  Results go to S.v.
+__device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im, const AxisGeom& g, int ox, int oy,
+                                               int nshift, bool shared_geom, int lane) {
+  int toff[SFE_SLOTS];
+  unsigned mx[SFE_SLOTS], mv[SFE_SLOTS];  // all-ones where the pixel uses x weights / vertical weights
+#pragma unroll 1
+  for (int s = 0; s < nshift; ++s) {
+    const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
+    if (s == 0 || !shared_geom) {
+      const int x0 = __shfl_sync(SFE_FULL, g.i0, jx), rx = __shfl_sync(SFE_FULL, g.r, jx);
+      const int y0 = __shfl_sync(SFE_FULL, g.i0, jy), ry = __shfl_sync(SFE_FULL, g.r, jy);
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const int i = lane + 32 * k;
+        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+        const bool valid = (k < SFE_SLOTS - 1 || i < SFE_PLEN) && pr >= ry && pc >= rx;
+        const int X = x0 + pc, Y = y0 + pr;
+        const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
+        int Xq = X;
+        if (!xin && !yin && Y < 0 && X >= im.w - 1 && im.w >= 2) Xq = im.w - 2;  // OpenCV top-right quirk
+        // the tile spans [ox, ox+15] x [oy, oy+15], already replicate-clamped; +1 / +TS stay inside
+        toff[k] = valid ? clampi(Y - oy, 0, 14) * TS + clampi(Xq - ox, 0, 14) : ZOFF;
+        mx[k] = xin ? 0xffffffffu : 0u;
+        mv[k] = (yin || !xin) ? 0xffffffffu : 0u;
+      }
+    }
+    const float axf = __shfl_sync(SFE_FULL, g.a, jx), ayf = __shfl_sync(SFE_FULL, g.a, jy);
+    const unsigned ax1 = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, jx)), ay1 = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, jy));
+    const unsigned one = 0x3f800000u;
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {
+      const float* t = S.tile + toff[k];
+      const unsigned r01 = __float_as_uint(t[1]), r10 = __float_as_uint(t[TS]), r11 = __float_as_uint(t[TS + 1]);
+      const float t00 = t[0], t01 = __uint_as_float(r01 & mx[k]);
+      const float t10 = __uint_as_float(r10 & mv[k]), t11 = __uint_as_float(r11 & mx[k] & mv[k]);
+      const float A1 = __uint_as_float((ax1 & mx[k]) | (one & ~mx[k])), B1 = __uint_as_float((ay1 & mv[k]) | (one & ~mv[k]));
+      S.v[(s * SFE_SLOTS + k) * 32 + lane] = fmaf(t11, axf * ayf, fmaf(t10, A1 * ayf, fmaf(t01, axf * B1, t00 * (A1 * B1))));
+    }
+  }
+}
+
+// Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
+// returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
+__device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
+  const bool h16 = lane & 16;
+  float r = (h16 ? b : a) + __shfl_xor_sync(SFE_FULL, h16 ? a : b, 16);
+  r = r + __shfl_xor_sync(SFE_FULL, r, 8);
+  r = r + __shfl_xor_sync(SFE_FULL, r, 4);
+  r = r + __shfl_xor_sync(SFE_FULL, r, 2);
+  return r + __shfl_xor_sync(SFE_FULL, r, 1);
+}
+
+// Finite differences of the six scores (hessian.h:163-169), lane-parallel.  Stage A: lane j < 8
+// forms q_j = [0.5 *] (score[P_j] - score[M_j]) / h; stage B: lane j < 4 forms (q[PB_j] - q[MB_j]) / h.
+// All arithmetic is IEEE double, operation for operation what the reference evaluates.  `sc` holds
+// score s in lanes 4s..4s+3 (the layout packed_reduce8 leaves).  d[6] = dx,dy,dxx,dxy,dyx,dyy.
+__device__ __forceinline__ void finite_differences(float sc, int lane, float (&d)[6]) {
+  constexpr unsigned PA = 0x55040343u, MA = 0x34201021u;  // minuend / subtrahend score of quotient j (nibbles)
+  constexpr unsigned PB = 0x7642u, MB = 0x4253u;          // dxx,dyy,dxy,dyx: minuend / subtrahend quotient
+  const double h = 0.02;
+  const int j = lane & 7;
+  const double p = (double)__shfl_sync(SFE_FULL, sc, 4 * ((PA >> (4 * j)) & 7));
+  const double m = (double)__shfl_sync(SFE_FULL, sc, 4 * ((MA >> (4 * j)) & 7));
+  double num = __dsub_rn(p, m);
+  if (j < 2) num = __dmul_rn(0.5, num);
+  const double q = __ddiv_rn(num, h);
+  const int jb = lane & 3;
+  const double qp = __shfl_sync(SFE_FULL, q, (PB >> (4 * jb)) & 7), qm = __shfl_sync(SFE_FULL, q, (MB >> (4 * jb)) & 7);
+  const double r = __ddiv_rn(__dsub_rn(qp, qm), h);
+  const float qf = (float)q, rf = (float)r;
+  d[0] = __shfl_sync(SFE_FULL, qf, 0);
+  d[1] = __shfl_sync(SFE_FULL, qf, 1);
+  d[2] = __shfl_sync(SFE_FULL, rf, 0);
+  d[5] = __shfl_sync(SFE_FULL, rf, 1);
+  d[3] = __shfl_sync(SFE_FULL, rf, 2);
+  d[4] = __shfl_sync(SFE_FULL, rf, 3);
+}
+
+struct Tmpl {
+  float T[SFE_SLOTS];    // the template patch (hessian.h:32-40)
+  float mkT[SFE_SLOTS];  // mask weight, 0 where the template pixel is exactly 0 (hessian.h:134)
+  float mean, sumsq;
+};
+
+// One patch evaluation at (x,y) of image `im`:
+//   is_tmpl   GetPatch (hessian.h:54-93): t <- the patch, its statistics and its effective mask
+//   otherwise BruteHessian (hessian.h:147-172) against the template t: the six derivatives
+//             d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as the reference stores them through
+//             float*); returns sad0.
+__device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool is_tmpl, Tmpl& t,
+                                          const float* __restrict__ mask, float x, float y, int lane, float (&d)[6]) {
+  __syncwarp();
+  const AxisGeom g = lane_geom(x, y, lane);
+  const int ox = (int)floorf(x) - 7, oy = (int)floorf(y) - 7;
+  const bool nonpos = stage_tile(S, im, ox, oy, lane);
+  const int ix = __shfl_sync(SFE_FULL, g.i0, 0), iy = __shfl_sync(SFE_FULL, g.i0, 4);
+  const bool mine = (lane & 3) != 3 && lane < 8;
+  const int ibase = __shfl_sync(SFE_FULL, g.i0, lane & 4), rbase = __shfl_sync(SFE_FULL, g.r, lane & 4);
+  const unsigned differ = __ballot_sync(SFE_FULL, mine && (g.i0 != ibase || g.r != rbase));  // shifts do not share taps
+  const unsigned clipped = __ballot_sync(SFE_FULL, mine && g.r != 0);
+  const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
+
+  // direct: the taps of every patch pixel are the plain 4-tap footprint (no border rule, no clipping)
+  const bool fast = differ == 0 && clipped == 0 && interior;
+  const bool direct = is_tmpl ? (interior && (clipped & 0x11u) == 0) : fast;
+  if (!direct) general_sample(S, im, g, ox, oy, is_tmpl ? 1 : 6, differ == 0, lane);
+
+  if (is_tmpl) {
+    float v[SFE_SLOTS];
+    if (direct) {
+      const float a = __shfl_sync(SFE_FULL, g.a, 0), a1 = __shfl_sync(SFE_FULL, g.a1, 0);
+      const float b = __shfl_sync(SFE_FULL, g.a, 4), b1 = __shfl_sync(SFE_FULL, g.a1, 4);
+      const float w0 = a1 * b1, w1 = a * b1, w2 = a1 * b, w3 = a * b;
+      const int base = (iy - oy) * TS + (ix - ox);
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const int i = lane + 32 * k;
+        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+        const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
+        v[k] = fmaf(tp[TS + 1], w3, fmaf(tp[TS], w2, fmaf(tp[1], w1, tp[0] * w0)));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) v[k] = S.v[k * 32 + lane];
+    }
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:85-91
+      sm = sm + v[k];
+      sq = fmaf(v[k], v[k], sq);
+      t.T[k] = v[k];
+      const float m = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
+      t.mkT[k] = v[k] == 0.f ? 0.f : m;
+    }
+    const float red = packed_reduce2(sm, sq, lane) / (float)SFE_PLEN;
+    t.mean = __shfl_sync(SFE_FULL, red, 0);
+    t.sumsq = __shfl_sync(SFE_FULL, red, 16);
+    return 0.f;
+  }
+
+  float v[6][SFE_SLOTS];
+  if (fast) {
+    // every patch pixel reads its 4 taps once; six weight sets
+    float ax[3], ax1[3], ay[3], ay1[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      ax[j] = __shfl_sync(SFE_FULL, g.a, j);
+      ax1[j] = __shfl_sync(SFE_FULL, g.a1, j);
+      ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
+      ay1[j] = __shfl_sync(SFE_FULL, g.a1, 4 + j);
+    }
+    float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
+    const int base = (iy - oy) * TS + (ix - ox);
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {
+      const int i = lane + 32 * k;
+      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+      const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
+      t00[k] = tp[0];
+      t01[k] = tp[1];
+      t10[k] = tp[TS];
+      t11[k] = tp[TS + 1];
+    }
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
+      const float w0 = ax1[jx] * ay1[jy], w1 = ax[jx] * ay1[jy], w2 = ax1[jx] * ay[jy], w3 = ax[jx] * ay[jy];
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 6; ++s)
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = S.v[(s * SFE_SLOTS + k) * 32 + lane];
+  }
+
+  // ---- common tail.  Patch statistics of the six candidates (hessian.h:85-91): 12 sums, one packed reduction
+  float st[16];
+#pragma unroll
+  for (int s = 0; s < 6; ++s) {
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {
+      sm = sm + v[s][k];
+      sq = fmaf(v[s][k], v[s][k], sq);
+    }
+    st[s] = sm;
+    st[8 + s] = sq;
+  }
+  st[6] = st[7] = st[14] = st[15] = 0.f;
+  const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
+  const float other = __shfl_xor_sync(SFE_FULL, red, 16);
+  // lane-parallel alpha/beta (hessian.h:131-132): lanes 2s (s < 6) hold the values of shift s; lanes >= 12
+  // hold padding and get benign operands so the IEEE divide/sqrt stay on their fast paths
+  const bool live = lane < 12;
+  const float mean = red / (float)SFE_PLEN, sumsq = live ? other / (float)SFE_PLEN : 1.f;
+  const float alpha_l = sqrtf((live ? t.sumsq : 1.f) / sumsq);
+  const float beta_l = t.mean - alpha_l * mean;
+  float part[8];
+  part[6] = part[7] = 0.f;
+  if (!(nonpos || clipped)) {
+    // no candidate pixel can be exactly 0 (strictly positive footprint, positive weights summing to 1)
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139
+        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+        diff = diff * diff;
+        p = fmaf(diff, t.mkT[k], p);
+      }
+      part[s] = p;
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+        diff = diff * diff;
+        const float q = fmaf(diff, t.mkT[k], p);
+        p = v[s][k] == 0.f ? p : q;
+      }
+      part[s] = p;
+    }
+  }
+  const float sc = packed_reduce8(part, lane);  // score s in lanes 4s..4s+3
+  finite_differences(sc, lane, d);
+  return __shfl_sync(SFE_FULL, sc, 0);
+}
+
+__device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
+  if (lane < TS + 2) S.zero[lane] = 0.f;
+  __syncwarp();
+}
+
+// GetPatches (hessian.h:175-183) on the template pyramid + TrackFeature (hessian.h:243-264) with Track
+// (hessian.h:185-241) on the search pyramid.  (x,y) is updated only on success.
+__device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, int tframe, float tx, float ty,
+                                             const PyrView& sp, int sframe, int levels, float thr, int maxit,
+                                             const float* __restrict__ mask, float& x, float& y, int lane, int& steps) {
+  const int lv = min(min(tp.depth, sp.depth), levels);
+  const float margin = 0.01f;
+  float px = x * (float)(1. / (1 << (lv - 1))), py = y * (float)(1. / (1 << (lv - 1)));
+#pragma unroll 1
+  for (int i = lv - 1; i >= 0; --i) {
+    const float sc = (float)(1. / (1 << i));  // pt *= 0.5 i times (exact)
+    Tmpl t;
+    t.mean = t.sumsq = 0.f;
+    const ImgView tim = img_of(tp, 0, i, tframe), sim = img_of(sp, 0, i, sframe);
+    // it == -1 extracts the template patch of this level (GetPatches); it >= 0 are the Newton steps
+#pragma unroll 1
+    for (int it = -1; it < maxit; ++it) {
+      const bool is_tmpl = it < 0;
+      if (!is_tmpl && (px < margin || py < margin || (px + margin) > (float)sim.w || (py + margin) > (float)sim.h))
+        return SFE_OUT_OF_BOUNDS;
+      ImgView im;
+      im.p = is_tmpl ? tim.p : sim.p;
+      im.w = sim.w; im.h = sim.h; im.pitch = sim.pitch;  // both pyramids have the same geometry
+      float d[6];
+      evaluate(S, im, is_tmpl, t, mask, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, d);
+      if (is_tmpl) continue;
+      ++steps;
+      float dx, dy;
+      newton_step(d[0], d[1], d[2], d[3], d[4], d[5], dx, dy);
+      px += clamp1(dx);
+      py += clamp1(dy);
+      if (fabsf(dx) < thr && fabsf(dy) < thr) break;
+    }
+    if (i > 0) { px *= 2.f; py *= 2.f; }
+  }
+  x = px;
+  y = py;
+  return SFE_OK;
+}
+
+// Persistent: the grid is sized to the machine (TRK_MINB CTAs per SM) and every warp pulls the next
+// feature from a global counter, so no warp slot idles while a CTA-mate finishes a feature that needs
+// more Newton steps (features take 8..80 steps; with static assignment a quarter of the slots idled).
+__global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrView from, PyrView to, TrackArgs a,
+                                                                           const float* __restrict__ mask,
+                                                                           int* __restrict__ next_feature) {
+  __shared__ WarpScratch scratch[TRK_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpScratch& S = scratch[warp];
+  init_scratch(S, lane);
+#pragma unroll 1
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(next_feature, 1);
+    i = __shfl_sync(SFE_FULL, i, 0);
+    if (i >= a.n) break;
+    const int pair = i / a.n_per_pair;
+    const int ff = a.from_first + pair, tf = a.to_first + pair;
+    const float fx = a.from_xy[2 * i], fy = a.from_xy[2 * i + 1];
+    float tx = a.to_xy[2 * i], ty = a.to_xy[2 * i + 1];
+    const int lv = a.levels ? a.levels[i] : a.default_levels;
+    int steps = 0;
+    int st[2];
+    float bx = fx, by = fy;  // matcher.cpp:181
+    // dir 0: template from `from` at from_pt, search `to` from the seed (matcher.cpp:175-176)
+    // dir 1: template from `to` at the forward result, search `from` from from_pt (matcher.cpp:180-182)
+    st[1] = SFE_OK;
+#pragma unroll 1
+    for (int dir = 0; dir < a.ndir; ++dir) {
+      const PyrView& tp = dir == 0 ? from : to;
+      const PyrView& sp = dir == 0 ? to : from;
+      float x = dir == 0 ? tx : bx, y = dir == 0 ? ty : by;
+      const int s = track_feature(S, tp, dir == 0 ? ff : tf, dir == 0 ? fx : tx, dir == 0 ? fy : ty, sp,
+                                  dir == 0 ? tf : ff, lv, a.thr, a.maxit, mask, x, y, lane, steps);
+      if (dir == 0) { tx = x; ty = y; st[0] = s; } else { bx = x; by = y; st[1] = s; }
+    }
+    bool ok = !(st[0] || st[1]);  // matcher.cpp:192
+    if (ok && a.ndir == 2) {
+      float ddx = fx - bx, ddy = fy - by;
+      double nrm = sqrt(__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)));
+      if (nrm > (double)a.fb_max) ok = false;  // matcher.cpp:201
+    }
+    if (lane == 0) {
+      a.to_xy[2 * i] = tx;
+      a.to_xy[2 * i + 1] = ty;
+      if (a.back_xy) { a.back_xy[2 * i] = bx; a.back_xy[2 * i + 1] = by; }
+      if (a.status_fwd) a.status_fwd[i] = st[0];
+      if (a.status_bwd) a.status_bwd[i] = st[1];
+      if (a.accepted) a.accepted[i] = ok ? 1 : 0;
+      if (a.steps) a.steps[i] = steps;
+    }
+  }
+}
+
 // GetPatch (hessian.h:54-93) for n points of one level
-__global__ void get_patches_kernel(PyrView v, int frame, int level, int n, const float* __restrict__ xy,
-                                   float* __restrict__ patches, float* __restrict__ mean, float* __restrict__ sumsq) {
+__global__ void __launch_bounds__(32 * TRK_WARPS) get_patches_kernel(PyrView v, int frame, int level, int n,
+                                                                     const float* __restrict__ xy, float* __restrict__ patches,
+                                                                     float* __restrict__ mean, float* __restrict__ sumsq) {
   __shared__ WarpScratch scratch[TRK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, i = blockIdx.x * TRK_WARPS + warp;
   if (i >= n) return;
   init_scratch(scratch[warp], lane);
-  float T[SFE_SLOTS], mk[SFE_SLOTS], d[6], m = 0.f, q = 0.f;
-  load_mask(nullptr, lane, mk);
-  evaluate<MODE_HESSIAN>(scratch[warp], img_of(v, 0, level, frame), true, T, m, q, mk, xy[2 * i], xy[2 * i + 1], lane, d);
+  float d[6];
+  Tmpl t;
+  evaluate(scratch[warp], img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, d);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
-    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = T[k];
-  if (lane == 0) { mean[i] = m; sumsq[i] = q; }
+    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = t.T[k];
+  if (lane == 0) { mean[i] = t.mean; sumsq[i] = t.sumsq; }
 }
 
 // BruteHessian (hessian.h:147-172) for n (template point, search point) pairs of one level
@@ -30,12 +443,10 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
   const int i = blockIdx.x * TRK_WARPS + warp;
   if (i >= n) return;
   init_scratch(scratch[warp], lane);
-  float mk[SFE_SLOTS];
-  load_mask(mask, lane, mk);
-  float T[SFE_SLOTS], m = 0.f, q = 0.f, d[6];
-  evaluate<MODE_HESSIAN>(scratch[warp], img_of(tv, 0, level, tframe), true, T, m, q, mk, txy[2 * i], txy[2 * i + 1], lane, d);
-  float s0 = evaluate<MODE_HESSIAN>(scratch[warp], img_of(sv, 0, level, sframe), false, T, m, q, mk, xy[2 * i],
-                                    xy[2 * i + 1], lane, d);
+  Tmpl t;
+  float d[6];
+  evaluate(scratch[warp], img_of(tv, 0, level, tframe), true, t, mask, txy[2 * i], txy[2 * i + 1], lane, d);
+  const float s0 = evaluate(scratch[warp], img_of(sv, 0, level, sframe), false, t, mask, xy[2 * i], xy[2 * i + 1], lane, d);
   if (lane == 0) {
     out7[7 * i] = s0;
     for (int k = 0; k < 6; ++k) out7[7 * i + 1 + k] = d[k];
@@ -44,24 +455,30 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
 
 }  // namespace
 
-int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask,
-                         int* counter, int num_sms, cudaStream_t s) {
-  return launch_track_fb<MODE_HESSIAN>(from, to, a, mask, counter, num_sms, s);
+int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a, const float* mask, int* counter,
+                         int num_sms, cudaStream_t s) {
+  if (a.n <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
+  if (e != cudaSuccess) return -(int)e;
+  const int blocks = min((a.n + TRK_WARPS - 1) / TRK_WARPS, num_sms * TRK_MINB);
+  track_fb_kernel<<<blocks, 32 * TRK_WARPS, 0, s>>>(from, to, a, mask, counter);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
 }
 
-int launch_get_patches(const PyrView& v, int frame, int level, int n, const float* xy, float* patches,
-                       float* mean, float* sumsq, cudaStream_t s) {
+int launch_get_patches(const PyrView& v, int frame, int level, int n, const float* xy, float* patches, float* mean,
+                       float* sumsq, cudaStream_t s) {
   if (n <= 0) return 0;
   get_patches_kernel<<<(n + TRK_WARPS - 1) / TRK_WARPS, 32 * TRK_WARPS, 0, s>>>(v, frame, level, n, xy, patches, mean, sumsq);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -(int)e;
 }
 
-int launch_brute_hessian(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level, int n,
-                         const float* txy, const float* xy, float* out7, const float* mask, cudaStream_t s) {
+int launch_brute_hessian(const PyrView& tv, int tframe, const PyrView& sv, int sframe, int level, int n, const float* txy,
+                         const float* xy, float* out7, const float* mask, cudaStream_t s) {
   if (n <= 0) return 0;
-  brute_hessian_kernel<<<(n + TRK_WARPS - 1) / TRK_WARPS, 32 * TRK_WARPS, 0, s>>>(tv, tframe, sv, sframe, level, n,
-                                                                                  txy, xy, out7, mask);
+  brute_hessian_kernel<<<(n + TRK_WARPS - 1) / TRK_WARPS, 32 * TRK_WARPS, 0, s>>>(tv, tframe, sv, sframe, level, n, txy, xy,
+                                                                                  out7, mask);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 1 : -(int)e;
 }
