@@ -32,6 +32,12 @@
 namespace {
 
 constexpr int TRK_WARPS = 4;
+#ifndef TRK_VSMEM
+#define TRK_VSMEM 0  // 1: candidate patch values of the fast route go through shared memory too
+#endif
+#ifndef TRK_TWO_SCORE
+#define TRK_TWO_SCORE 0  // 1: a second, select-free score loop for footprints without zeros (fewer instructions, +5 KB code)
+#endif
 #ifndef TRK_MINB
 #define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
 #endif
@@ -123,6 +129,31 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
   }
 }
 
+// Straddle route: no border rule and no clipping, but a +-h shift crosses an integer boundary, so the
+// shifts do not share their taps: a compact runtime loop re-reads the 4 taps per shift.  Results go to S.v.
+__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int lane) {
+  int poff[SFE_SLOTS];
+#pragma unroll
+  for (int k = 0; k < SFE_SLOTS; ++k) {
+    const int i = lane + 32 * k;
+    const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+    poff[k] = (k < SFE_SLOTS - 1 || i < SFE_PLEN) ? pr * TS + pc : -1;
+  }
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
+    const int base = (__shfl_sync(SFE_FULL, g.i0, jy) - oy) * TS + (__shfl_sync(SFE_FULL, g.i0, jx) - ox);
+    const float ax = __shfl_sync(SFE_FULL, g.a, jx), ax1 = __shfl_sync(SFE_FULL, g.a1, jx);
+    const float ay = __shfl_sync(SFE_FULL, g.a, jy), ay1 = __shfl_sync(SFE_FULL, g.a1, jy);
+    const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {
+      const float* tp = S.tile + (poff[k] >= 0 ? base + poff[k] : ZOFF);
+      S.v[(s * SFE_SLOTS + k) * 32 + lane] = fmaf(tp[TS + 1], w3, fmaf(tp[TS], w2, fmaf(tp[1], w1, tp[0] * w0)));
+    }
+  }
+}
+
 // Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
 // returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
 __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
@@ -186,8 +217,16 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
 
   // direct: the taps of every patch pixel are the plain 4-tap footprint (no border rule, no clipping)
   const bool fast = differ == 0 && clipped == 0 && interior;
+  // straddle: as fast, but some shift has its integer origin one pixel off (all origins within +-1 stay inside)
+  const bool straddle = !is_tmpl && differ != 0 && clipped == 0 && ix >= 1 && ix + SFE_PATCH + 1 <= im.w - 1 && iy >= 1 &&
+                        iy + SFE_PATCH + 1 <= im.h - 1;
   const bool direct = is_tmpl ? (interior && (clipped & 0x11u) == 0) : fast;
-  if (!direct) general_sample(S, im, g, ox, oy, is_tmpl ? 1 : 6, differ == 0, lane);
+  if (straddle) straddle_sample(S, g, ox, oy, lane);
+  else if (!direct) {
+    int nshift = is_tmpl ? 1 : 6;
+    asm volatile("" : "+r"(nshift));  // opaque: one copy of the loop serves both callers (code size)
+    general_sample(S, im, g, ox, oy, nshift, differ == 0, lane);
+  }
 
   if (is_tmpl) {
     float v[SFE_SLOTS];
@@ -222,6 +261,63 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
     return 0.f;
   }
 
+  // ---- sampling + patch statistics of the six candidates (hessian.h:85-91): 12 partial sums per lane
+  float st[16];
+#if TRK_VSMEM
+  // patch values live in the shared scratch for every route (fewer registers, more resident warps)
+#define VLOAD(s, k) S.v[((s) * SFE_SLOTS + (k)) * 32 + lane]
+  if (fast) {
+    float ax[3], ax1[3], ay[3], ay1[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      ax[j] = __shfl_sync(SFE_FULL, g.a, j);
+      ax1[j] = __shfl_sync(SFE_FULL, g.a1, j);
+      ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
+      ay1[j] = __shfl_sync(SFE_FULL, g.a1, 4 + j);
+    }
+    float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
+    const int base = (iy - oy) * TS + (ix - ox);
+#pragma unroll
+    for (int k = 0; k < SFE_SLOTS; ++k) {
+      const int i = lane + 32 * k;
+      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+      const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
+      t00[k] = tp[0];
+      t01[k] = tp[1];
+      t10[k] = tp[TS];
+      t11[k] = tp[TS + 1];
+    }
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
+      const float w0 = ax1[jx] * ay1[jy], w1 = ax[jx] * ay1[jy], w2 = ax1[jx] * ay[jy], w3 = ax[jx] * ay[jy];
+      float sm = 0.f, sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const float vv = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+        VLOAD(s, k) = vv;
+        sm = sm + vv;
+        sq = fmaf(vv, vv, sq);
+      }
+      st[s] = sm;
+      st[8 + s] = sq;
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      float sm = 0.f, sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const float vv = VLOAD(s, k);
+        sm = sm + vv;
+        sq = fmaf(vv, vv, sq);
+      }
+      st[s] = sm;
+      st[8 + s] = sq;
+    }
+  }
+#else
+#define VLOAD(s, k) v[s][k]
   float v[6][SFE_SLOTS];
   if (fast) {
     // every patch pixel reads its 4 taps once; six weight sets
@@ -258,9 +354,6 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = S.v[(s * SFE_SLOTS + k) * 32 + lane];
   }
-
-  // ---- common tail.  Patch statistics of the six candidates (hessian.h:85-91): 12 sums, one packed reduction
-  float st[16];
 #pragma unroll
   for (int s = 0; s < 6; ++s) {
     float sm = 0.f, sq = 0.f;
@@ -272,6 +365,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
     st[s] = sm;
     st[8 + s] = sq;
   }
+#endif
   st[6] = st[7] = st[14] = st[15] = 0.f;
   const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
   const float other = __shfl_xor_sync(SFE_FULL, red, 16);
@@ -283,6 +377,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   const float beta_l = t.mean - alpha_l * mean;
   float part[8];
   part[6] = part[7] = 0.f;
+#if TRK_TWO_SCORE
   if (!(nonpos || clipped)) {
     // no candidate pixel can be exactly 0 (strictly positive footprint, positive weights summing to 1)
 #pragma unroll
@@ -291,23 +386,26 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139
-        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+        float diff = fmaf(-VLOAD(s, k), alpha, t.T[k]) - beta;
         diff = diff * diff;
         p = fmaf(diff, t.mkT[k], p);
       }
       part[s] = p;
     }
-  } else {
+  } else
+#endif
+  {
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
       float p = 0.f;
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+      for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139; template zeros are folded into mkT
+        const float vv = VLOAD(s, k);
+        float diff = fmaf(-vv, alpha, t.T[k]) - beta;
         diff = diff * diff;
         const float q = fmaf(diff, t.mkT[k], p);
-        p = v[s][k] == 0.f ? p : q;
+        p = vv == 0.f ? p : q;
       }
       part[s] = p;
     }
@@ -315,6 +413,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   const float sc = packed_reduce8(part, lane);  // score s in lanes 4s..4s+3
   finite_differences(sc, lane, d);
   return __shfl_sync(SFE_FULL, sc, 0);
+#undef VLOAD
 }
 
 __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
