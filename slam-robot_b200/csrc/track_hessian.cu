@@ -12,32 +12,27 @@
 // packed warp reduction -> lane-parallel alpha/beta -> scores -> packed reduction -> lane-parallel
 // finite differences):
 //   fast      all six shifts share their integer taps, no GetPatch clipping, footprint inside the
-//             image: every lane loads the 4 taps of its <= 6 patch pixels once and evaluates six
-//             weight sets (fully unrolled, patch values stay in registers);
+//             image and strictly positive: every lane loads the 4 taps of its <= 6 patch pixels once
+//             and evaluates six weight sets (fully unrolled, patch values stay in registers);
+//   plain     as fast, but a shift crosses an integer boundary or the footprint holds a zero: a compact
+//             runtime loop over the shifts re-reads the taps and writes the patch values to a per-warp
+//             shared scratch; template patches (GetPatch, one shift) take one iteration of it;
 //   general   image borders (cv::getRectSubPix's per-pixel 2-tap rules and its top-right
-//             irregularity), GetPatch's left/top clipping, or a shift that crosses an integer
-//             boundary: a compact runtime loop over the shifts writes the patch values to a per-warp
-//             shared scratch, from which the common tail reads them back;
-//   template  GetPatch of the template patch (one shift): a 4-tap pass straight from the tile, or
-//             one iteration of the general loop.
+//             irregularity) and GetPatch's left/top clipping, same scratch.
 // The exact-zero skip of ScorePatchMatch (hessian.h:134) is folded away where it cannot trigger:
 // template zeros become zero mask weights once per level (x*0 adds an exact zero), and candidate
-// zeros are impossible when the staged footprint is strictly positive and nothing is clipped, so
-// only footprints that contain a zero run the select variant of the score loop.
+// zeros are impossible when the staged footprint is strictly positive and nothing is clipped; the
+// remaining cases run a compact rolled score loop with the select.
 //
 // Code size is a first-class constraint: every warp sits at a different point of a long dependent
-// chain, so the body has to stay inside the 32 KB L1.5 instruction cache (profiles/README.md).
+// chain, so the frequently executed body has to stay inside the 32 KB L1.5 instruction cache.  Measured
+// (profiles/README.md): +376 SASS instructions across that line cost +14 % run time although they
+// removed 5 % of the executed instructions; below the line, fewer executed instructions win again.
 #include "patch.cuh"
 
 namespace {
 
 constexpr int TRK_WARPS = 4;
-#ifndef TRK_VSMEM
-#define TRK_VSMEM 0  // 1: candidate patch values of the fast route go through shared memory too
-#endif
-#ifndef TRK_TWO_SCORE
-#define TRK_TWO_SCORE 0  // 1: a second, select-free score loop for footprints without zeros (fewer instructions, +5 KB code)
-#endif
 #ifndef TRK_MINB
 #define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
 #endif
@@ -129,9 +124,10 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
   }
 }
 
-// Straddle route: no border rule and no clipping, but a +-h shift crosses an integer boundary, so the
-// shifts do not share their taps: a compact runtime loop re-reads the 4 taps per shift.  Results go to S.v.
-__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int lane) {
+// Plain route: no border rule and no clipping.  A compact runtime loop re-reads the 4 taps per shift, so it
+// also serves steps in which a +-h shift crosses an integer boundary (the shifts do not share their taps
+// then), template patches (one shift) and footprints that contain a zero.  Results go to S.v.
+__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int nshift, int lane) {
   int poff[SFE_SLOTS];
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k) {
@@ -140,7 +136,7 @@ __device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& 
     poff[k] = (k < SFE_SLOTS - 1 || i < SFE_PLEN) ? pr * TS + pc : -1;
   }
 #pragma unroll 1
-  for (int s = 0; s < 6; ++s) {
+  for (int s = 0; s < nshift; ++s) {
     const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
     const int base = (__shfl_sync(SFE_FULL, g.i0, jy) - oy) * TS + (__shfl_sync(SFE_FULL, g.i0, jx) - ox);
     const float ax = __shfl_sync(SFE_FULL, g.a, jx), ax1 = __shfl_sync(SFE_FULL, g.a1, jx);
@@ -215,45 +211,30 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   const unsigned clipped = __ballot_sync(SFE_FULL, mine && g.r != 0);
   const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
 
-  // direct: the taps of every patch pixel are the plain 4-tap footprint (no border rule, no clipping)
-  const bool fast = differ == 0 && clipped == 0 && interior;
-  // straddle: as fast, but some shift has its integer origin one pixel off (all origins within +-1 stay inside)
-  const bool straddle = !is_tmpl && differ != 0 && clipped == 0 && ix >= 1 && ix + SFE_PATCH + 1 <= im.w - 1 && iy >= 1 &&
-                        iy + SFE_PATCH + 1 <= im.h - 1;
-  const bool direct = is_tmpl ? (interior && (clipped & 0x11u) == 0) : fast;
-  if (straddle) straddle_sample(S, g, ox, oy, lane);
-  else if (!direct) {
+  // fast: no border rule, no clipping, all six shifts share their taps, and no pixel can be exactly 0 (a strictly
+  // positive footprint under positive weights that sum to 1) -- patch values stay in registers.
+  // plain: no border rule / clipping for any shift (integer origins within +-1 of the unshifted one).
+  const bool zeros = nonpos || clipped != 0;
+  const bool fast = !is_tmpl && differ == 0 && !zeros && interior;
+  const bool plain = is_tmpl ? (interior && (clipped & 0x11u) == 0)
+                             : (clipped == 0 && ix >= 1 && ix + SFE_PATCH + 1 <= im.w - 1 && iy >= 1 && iy + SFE_PATCH + 1 <= im.h - 1);
+  if (!fast) {
     int nshift = is_tmpl ? 1 : 6;
-    asm volatile("" : "+r"(nshift));  // opaque: one copy of the loop serves both callers (code size)
-    general_sample(S, im, g, ox, oy, nshift, differ == 0, lane);
+    asm volatile("" : "+r"(nshift));  // opaque: one copy of each loop serves both callers (code size)
+    if (plain) straddle_sample(S, g, ox, oy, nshift, lane);
+    else general_sample(S, im, g, ox, oy, nshift, differ == 0, lane);
   }
 
   if (is_tmpl) {
-    float v[SFE_SLOTS];
-    if (direct) {
-      const float a = __shfl_sync(SFE_FULL, g.a, 0), a1 = __shfl_sync(SFE_FULL, g.a1, 0);
-      const float b = __shfl_sync(SFE_FULL, g.a, 4), b1 = __shfl_sync(SFE_FULL, g.a1, 4);
-      const float w0 = a1 * b1, w1 = a * b1, w2 = a1 * b, w3 = a * b;
-      const int base = (iy - oy) * TS + (ix - ox);
-#pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        const int i = lane + 32 * k;
-        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-        const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
-        v[k] = fmaf(tp[TS + 1], w3, fmaf(tp[TS], w2, fmaf(tp[1], w1, tp[0] * w0)));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) v[k] = S.v[k * 32 + lane];
-    }
     float sm = 0.f, sq = 0.f;
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:85-91
-      sm = sm + v[k];
-      sq = fmaf(v[k], v[k], sq);
-      t.T[k] = v[k];
+      const float v = S.v[k * 32 + lane];
+      sm = sm + v;
+      sq = fmaf(v, v, sq);
+      t.T[k] = v;
       const float m = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
-      t.mkT[k] = v[k] == 0.f ? 0.f : m;
+      t.mkT[k] = v == 0.f ? 0.f : m;
     }
     const float red = packed_reduce2(sm, sq, lane) / (float)SFE_PLEN;
     t.mean = __shfl_sync(SFE_FULL, red, 0);
@@ -263,61 +244,6 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
 
   // ---- sampling + patch statistics of the six candidates (hessian.h:85-91): 12 partial sums per lane
   float st[16];
-#if TRK_VSMEM
-  // patch values live in the shared scratch for every route (fewer registers, more resident warps)
-#define VLOAD(s, k) S.v[((s) * SFE_SLOTS + (k)) * 32 + lane]
-  if (fast) {
-    float ax[3], ax1[3], ay[3], ay1[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      ax[j] = __shfl_sync(SFE_FULL, g.a, j);
-      ax1[j] = __shfl_sync(SFE_FULL, g.a1, j);
-      ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
-      ay1[j] = __shfl_sync(SFE_FULL, g.a1, 4 + j);
-    }
-    float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
-    const int base = (iy - oy) * TS + (ix - ox);
-#pragma unroll
-    for (int k = 0; k < SFE_SLOTS; ++k) {
-      const int i = lane + 32 * k;
-      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-      const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
-      t00[k] = tp[0];
-      t01[k] = tp[1];
-      t10[k] = tp[TS];
-      t11[k] = tp[TS + 1];
-    }
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
-      const float w0 = ax1[jx] * ay1[jy], w1 = ax[jx] * ay1[jy], w2 = ax1[jx] * ay[jy], w3 = ax[jx] * ay[jy];
-      float sm = 0.f, sq = 0.f;
-#pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        const float vv = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
-        VLOAD(s, k) = vv;
-        sm = sm + vv;
-        sq = fmaf(vv, vv, sq);
-      }
-      st[s] = sm;
-      st[8 + s] = sq;
-    }
-  } else {
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      float sm = 0.f, sq = 0.f;
-#pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {
-        const float vv = VLOAD(s, k);
-        sm = sm + vv;
-        sq = fmaf(vv, vv, sq);
-      }
-      st[s] = sm;
-      st[8 + s] = sq;
-    }
-  }
-#else
-#define VLOAD(s, k) v[s][k]
   float v[6][SFE_SLOTS];
   if (fast) {
     // every patch pixel reads its 4 taps once; six weight sets
@@ -365,7 +291,6 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
     st[s] = sm;
     st[8 + s] = sq;
   }
-#endif
   st[6] = st[7] = st[14] = st[15] = 0.f;
   const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
   const float other = __shfl_xor_sync(SFE_FULL, red, 16);
@@ -377,43 +302,42 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   const float beta_l = t.mean - alpha_l * mean;
   float part[8];
   part[6] = part[7] = 0.f;
-#if TRK_TWO_SCORE
-  if (!(nonpos || clipped)) {
-    // no candidate pixel can be exactly 0 (strictly positive footprint, positive weights summing to 1)
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
-      float p = 0.f;
-#pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139
-        float diff = fmaf(-VLOAD(s, k), alpha, t.T[k]) - beta;
-        diff = diff * diff;
-        p = fmaf(diff, t.mkT[k], p);
-      }
-      part[s] = p;
-    }
-  } else
-#endif
-  {
+  if (!zeros) {
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139; template zeros are folded into mkT
-        const float vv = VLOAD(s, k);
+        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+        diff = diff * diff;
+        p = fmaf(diff, t.mkT[k], p);
+      }
+      part[s] = p;
+    }
+  } else {
+    // candidate pixels may be exactly 0 (hessian.h:134 skips them): rare, so a compact rolled loop over S.v
+#pragma unroll
+    for (int j = 0; j < 6; ++j) part[j] = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < SFE_SLOTS; ++k) {
+        const float vv = S.v[(s * SFE_SLOTS + k) * 32 + lane];
         float diff = fmaf(-vv, alpha, t.T[k]) - beta;
         diff = diff * diff;
         const float q = fmaf(diff, t.mkT[k], p);
         p = vv == 0.f ? p : q;
       }
-      part[s] = p;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) part[j] = s == j ? p : part[j];
     }
   }
   const float sc = packed_reduce8(part, lane);  // score s in lanes 4s..4s+3
   finite_differences(sc, lane, d);
   return __shfl_sync(SFE_FULL, sc, 0);
-#undef VLOAD
 }
 
 __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {

@@ -108,6 +108,42 @@ def test_track_fb_bit_exact(fe, po, pair640, synth, levels):
     assert np.median(err) < 0.1
 
 
+def test_track_fb_black_regions_bit_exact(fe, po, synth):
+    """Frames with saturated-black blocks: the blurred planes hold exact zeros, so ScorePatchMatch's
+    exact-zero skip (hessian.h:134) triggers for candidate and template pixels -- the routes of the CUDA
+    tracker that fold the skip away must not be taken there."""
+    H, W = 240, 320
+    A, B = synth.make_pairs(17, 1, H, W)
+    A, B = A[0].numpy().copy(), B[0].numpy().copy()
+    rng = np.random.default_rng(4)
+    for img, sh in ((A, 0), (B, 2)):
+        for (y, x) in ((40, 60), (150, 200), (100, 20), (0, 250), (200, 0)):
+            img[y + sh:y + sh + 40, x + sh:x + sh + 48] = 0
+    n = 400
+    pts = _features(synth, n, H, W, seed=8, border=0.1)
+    # half of the features sit on the edges of the black blocks
+    edges = np.float32([[60, 40], [108, 80], [200, 150], [248, 190], [20, 100], [68, 140], [250, 0], [298, 40], [0, 200], [48, 239]])
+    pts[: n // 2] = (edges[rng.integers(0, len(edges), n // 2)] + rng.uniform(-9, 9, (n // 2, 2))).clip(1, [W - 2, H - 2]).astype(np.float32)
+    ga, gb = fe.make_pyramid(A, 4), fe.make_pyramid(B, 4)
+    oa, ob = po.Pyramid(A, 4), po.Pyramid(B, 4)
+    assert (oa.plane(0) == 0).sum() > 1000 and (oa.plane(2) == 0).sum() > 10   # the zeros are really there
+    g = fe.track_fb(ga, gb, pts, pts, 4)
+    o = po.hes_track_fb(oa, ob, pts, pts, 4)
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(g[k], o[k]), k
+    # NaN positions (all-black patches: 0/0 statistics) must match as bit patterns too
+    assert_bits_equal(g["to_xy"], o["to_xy"], "to_xy")
+    assert_bits_equal(g["back_xy"], o["back_xy"], "back_xy")
+    assert int(g["steps"].sum()) == o["newton_steps"]
+    for level in (0, 2):
+        s = np.float32(0.5 ** level)
+        out = fe.brute_hessian(ga, gb, level, pts[:200] * s, pts[:200] * s + np.float32(0.3))
+        for i in range(200):
+            d, m, q = po.hes_get_patch(oa, level, pts[i, 0] * s, pts[i, 1] * s)
+            s0, d6 = po.hes_brute_hessian(ob, level, d, m, q, pts[i, 0] * s + np.float32(0.3), pts[i, 1] * s + np.float32(0.3))
+            assert_bits_equal(out[i], np.concatenate([[s0], d6]).astype(np.float32), "BruteHessian level %d #%d" % (level, i))
+
+
 def test_track_fb_batched_pairs(fe, po, synth):
     """n_per_pair batching: 3 independent pairs in one call == three single-pair oracle runs."""
     H, W = 240, 320
