@@ -14,7 +14,7 @@
 //                    filters run out of shared memory, the level is written once.
 #include <stdlib.h>
 
-#include "sfe_common.cuh"
+#include "pyr_math.cuh"
 
 namespace {
 
@@ -25,28 +25,6 @@ __device__ __forceinline__ float gray_f32(const uint8_t* px) {
   // cvtColor(RGB2GRAY) on BGR bytes (hessian.h:100) then convertTo(CV_32F, 1/255.) (hessian.h:101)
   int g = (9798 * px[0] + 19235 * px[1] + 3735 * px[2] + (1 << 14)) >> 15;
   return (float)g * (float)(1. / 255.);
-}
-
-struct Taps { float k0, k1, k2; };
-
-// cv::getGaussianKernel(5, sigma, CV_32F) bit patterns (oracle.c gauss_taps)
-__host__ __device__ inline Taps taps_for(int which) {
-  Taps t;
-  if (which == 0) { t.k0 = __builtin_bit_cast(float, 0x3ebd3532u); t.k1 = __builtin_bit_cast(float, 0x3e7a53d4u); t.k2 = __builtin_bit_cast(float, 0x3d90edf6u); }       // 1.1
-  else if (which == 1) { t.k0 = __builtin_bit_cast(float, 0x3eff8c30u); t.k1 = __builtin_bit_cast(float, 0x3e69ff17u); t.k2 = __builtin_bit_cast(float, 0x3cb3a5ccu); }  // 0.8
-  else { t.k0 = __builtin_bit_cast(float, 0x3f29efffu); t.k1 = __builtin_bit_cast(float, 0x3e297f46u); t.k2 = __builtin_bit_cast(float, 0x3b282ed8u); }                  // 0.6
-  return t;
-}
-
-__device__ __forceinline__ float blur_row(float m2, float m1, float c, float p1, float p2, Taps t) {
-  float r = (m1 + p1) * t.k1;
-  r = fmaf(t.k0, c, r);
-  return fmaf(t.k2, m2 + p2, r);
-}
-__device__ __forceinline__ float blur_col(float m2, float m1, float c, float p1, float p2, Taps t) {
-  float r = c * t.k0;
-  r = fmaf(t.k1, m1 + p1, r);
-  return fmaf(t.k2, m2 + p2, r);
 }
 
 // ------------------------------------------------------------------------------- level 0
@@ -303,13 +281,6 @@ struct DownTile {
   static constexpr size_t SMEM = sizeof(float) * ((size_t)PH * PW + (size_t)PH * PDW);
 };
 
-__device__ __forceinline__ float pd_h(float m2, float m1, float c, float p1, float p2) {
-  return ((m2 + p2) + (m1 + p1) * 4.f) + c * 6.f;
-}
-__device__ __forceinline__ float pd_v(float r0, float r1, float r2, float r3, float r4) {
-  return (((r1 + r3) + r2) * 4.f + ((r0 + r4) + (r2 + r2))) * (1.f / 256.f);
-}
-
 template <int D_TW, int D_TH>
 __global__ void __launch_bounds__(D_THREADS) pyr_down_blur_fast(const float* __restrict__ prev_base, long long prev_fs,
                                                                 int pw, int ph, int ppitch, float* __restrict__ cur_base,
@@ -453,17 +424,24 @@ void launch_down_fast(const PyrView& v, int l, int first, int count, int blur_id
 int build_chunk(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first,
                 int count, cudaStream_t s) {
   int launches = 0;
+  // streaming path (pyramid_stream.cu): levels 0+1 fused, deeper levels while their geometry qualifies
+  static const bool tiled_only = getenv("SFE_PYR_TILED") != nullptr;
+  int built = 0;
+  if (flavor == SFE_HESSIAN && !tiled_only)
+    built = launch_pyr_stream_hessian(v, bgr, row_stride, frame_stride, first, count, s, &launches);
   dim3 g0((v.w[0] + L0_TW - 1) / L0_TW, (v.h[0] + L0_TH - 1) / L0_TH, count);
   const bool fast_l0 = flavor == SFE_HESSIAN && v.w[0] % 4 == 0 && ((uintptr_t)bgr & 3) == 0 && row_stride % 4 == 0 &&
                        frame_stride % 4 == 0;
-  if (fast_l0) {
+  if (built > 0) {
+    --launches;  // level 0 came with the streaming kernel (the increment below counts this branch's launch)
+  } else if (fast_l0) {
     dim3 gf((v.w[0] + F_TW - 1) / F_TW, (v.h[0] + F_TH - 1) / F_TH, count);
     pyr_l0_hessian_fast<<<gf, F_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
   } else if (flavor == SFE_HESSIAN) pyr_l0_kernel<SFE_HESSIAN><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
   else if (flavor == SFE_KLT) pyr_l0_kernel<SFE_KLT><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
   else pyr_l0_kernel<SFE_BRUTE><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
   ++launches;
-  for (int l = 1; l < v.depth; ++l) {
+  for (int l = built > 0 ? built : 1; l < v.depth; ++l) {
     dim3 g((v.w[l] + DN_TW - 1) / DN_TW, (v.h[l] + DN_TH - 1) / DN_TH, count);
     int blur_id = flavor == SFE_HESSIAN ? 1 : (flavor == SFE_KLT ? 2 : -1);
     // fast path: blurred plane, both levels 4-float aligned, level at least one blur reach wide/high

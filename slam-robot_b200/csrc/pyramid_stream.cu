@@ -1,0 +1,270 @@
+// pyramid_stream.cu -- MakePyramid (hessian.h:95-126) as a register-streaming pipeline.
+//
+// Why: the tiled kernels in pyramid.cu spend their time on instruction issue (index arithmetic, shared
+// memory round trips, 1.3-1.4x halo recomputation) and re-read level 0 from HBM to build level 1.
+// Here one WARP owns a column strip of a frame (128 level-0 columns, 112 of them useful) and walks down
+// its rows; nothing is staged in shared memory:
+//   * horizontal filters exchange the two or three neighbouring pixels with warp shuffles;
+//   * vertical filters keep their last five rows in registers (the row loop is unrolled ten-fold so the
+//     window slots are compile-time register names);
+//   * level 0 (gray -> /255 -> 5x5 blur) and level 1 (pyrDown -> 5x5 blur) are fused: the level-0 row a
+//     lane has just produced feeds the level-1 pipeline directly, so the BGR bytes are read once and
+//     every level is written once (algorithmic HBM traffic); deeper levels run the same down stage
+//     from the previous level's floats.
+// Borders (cv::BORDER_REFLECT_101): above the image the strip simply starts eight rows early on the
+// reflected rows -- every filter is symmetric in its taps, so the extension reproduces the reflected
+// values bit for bit.  That trick does not carry across a downsampling step at the right/bottom edge
+// (the mirror axes of the two grids differ), so there the last in-image lane takes its out-of-image
+// neighbours from the mirrored pixels it already holds, and the last two level-1 rows take their
+// out-of-image pyrDown rows from the mirrored rows still in the window.
+// The arithmetic per pixel is pyr_math.cuh's, i.e. bit-identical to the tiled kernels and the oracle.
+#include "pyr_math.cuh"
+
+namespace {
+
+constexpr int STRIP_USEFUL = 112;  // level-(l-1) columns a strip contributes: lanes 2..29, 4 columns each
+constexpr int STRIP_HALO = 8;      // two dead lanes on each side absorb the 8-column reach of blur o pyrDown o blur
+
+struct StreamArgs {
+  const uint8_t* bgr;      // FROM_BGR input: 8-bit interleaved frames (frame 0 = first frame of this call)
+  size_t row_stride, frame_stride;
+  const float* in;         // !FROM_BGR input: level l-1 planes of the pyramid batch
+  long long in_fs;
+  int in_pitch;
+  float* out0;             // FROM_BGR: level 0 planes
+  long long out0_fs;
+  int out0_pitch;
+  float* out1;             // the downsampled level
+  long long out1_fs;
+  int out1_pitch;
+  int w, h;                // size of the input level (level 0 for FROM_BGR); w % 4 == 0
+  int w1, h1;              // size of the downsampled level: w/2, (h+1)/2
+  int first;               // first frame slot in the pyramid batch
+  int strips, bands, band_rows, nunits;
+  int blur0, blur1;        // tap sets of the two Gaussian blurs
+};
+
+__device__ __forceinline__ float gray_px(uint32_t p) {
+  // cvtColor(RGB2GRAY) on BGR bytes (hessian.h:100), then convertTo(CV_32F, 1/255.) (hessian.h:101)
+  unsigned s = __dp2a_lo(9798u | (19235u << 16), p, 1u << 14);
+  s = __dp2a_hi(3735u, p, s);
+  return (float)(int)(s >> 15) * (float)(1. / 255.);
+}
+
+__device__ __forceinline__ int reflect_row(int t, int h) {
+  t = t < 0 ? -t : t;
+  t = t >= h ? 2 * (h - 1) - t : t;
+  return min(max(t, 0), h - 1);  // the clamp only matters for ticks whose results are never stored
+}
+
+template <bool FROM_BGR>
+struct RawRow;
+template <>
+struct RawRow<true> { uint32_t a, b, c; };
+template <>
+struct RawRow<false> { float4 v; };
+
+template <bool FROM_BGR>
+__device__ __forceinline__ void load_row(RawRow<FROM_BGR>& r, const StreamArgs& a, const uint8_t* bgr_px, const float* in_px,
+                                         int t, bool inimg) {
+  const int ry = reflect_row(t, a.h);
+  if constexpr (FROM_BGR) {
+    r.a = r.b = r.c = 0u;
+    if (inimg) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(bgr_px + (size_t)ry * a.row_stride);
+      r.a = __ldg(p);
+      r.b = __ldg(p + 1);
+      r.c = __ldg(p + 2);
+    }
+  } else {
+    r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inimg) r.v = __ldg(reinterpret_cast<const float4*>(in_px + (size_t)ry * a.in_pitch));
+  }
+}
+
+// One warp = one (frame, row band, column strip) unit.
+template <bool FROM_BGR>
+__global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
+  const int lane = threadIdx.x;
+  const int unit = blockIdx.x;
+  const int strip = unit % a.strips;
+  const int band = (unit / a.strips) % a.bands;
+  const int frame = unit / (a.strips * a.bands);
+
+  const int g = STRIP_USEFUL * strip - STRIP_HALO + 4 * lane;  // first input column of this lane
+  const bool inimg = g >= 0 && g < a.w;                        // w % 4 == 0: the group is all in or all out
+  const bool ledge = g == 0, redge = g == a.w - 4;
+  const bool useful = inimg && lane >= 2 && lane <= 29;
+  const int r0 = band * a.band_rows;                           // band of input rows [r0, r1); band_rows is even
+  const int r1 = min(r0 + a.band_rows, 2 * a.h1);
+  const int q_hi = min(r1, a.h), j_lo = r0 >> 1, j_hi = min(r1 >> 1, a.h1);
+  const Taps k0 = taps_for(a.blur0), k1 = taps_for(a.blur1);
+
+  const uint8_t* bgr_px = nullptr;
+  const float* in_px = nullptr;
+  float* out0_px = nullptr;
+  if constexpr (FROM_BGR) {
+    bgr_px = a.bgr + (size_t)frame * a.frame_stride + 3 * (size_t)max(g, 0);
+    out0_px = a.out0 + (long long)(a.first + frame) * a.out0_fs + max(g, 0);
+  } else {
+    in_px = a.in + (long long)(a.first + frame) * a.in_fs + max(g, 0);
+  }
+  float* out1_px = a.out1 + (long long)(a.first + frame) * a.out1_fs + (max(g, 0) >> 1);
+
+  // Ticks: at tick t the input row t arrives (FROM_BGR: its horizontally blurred gray row, which completes
+  // level-0 row q = t-2; otherwise the previous level's row q = t).  pyrDown row i needs rows 2i-2..2i+2 and is
+  // formed at q = 2i+2; downsampled row j needs pyrDown rows j-2..j+2 and is formed with i = j+2.
+  constexpr int LAG = FROM_BGR ? 2 : 0;
+  const int t_begin = r0 - 8;  // even, so q is even exactly when the unrolled tick index is
+  const int t_last = r1 + 4 + LAG;
+  RawRow<FROM_BGR> raw[5];
+#pragma unroll
+  for (int u = 0; u < 5; ++u) load_row<FROM_BGR>(raw[u], a, bgr_px, in_px, t_begin + u, inimg);
+
+  float4 hbw[5];   // FROM_BGR: horizontally blurred gray rows t-4..t
+  float2 phw[5];   // horizontally pyrDown-filtered rows q-4..q
+  float2 bhw[5];   // horizontally blurred pyrDown rows i-4..i
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    hbw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    phw[u] = bhw[u] = make_float2(0.f, 0.f);
+  }
+
+#pragma unroll 1
+  for (int tb = t_begin; tb <= t_last; tb += 10) {
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int t = tb + u;
+      const int q = t - LAG;
+      float4 row;
+      if constexpr (FROM_BGR) {
+        const RawRow<true> rr = raw[u % 5];
+        load_row<true>(raw[u % 5], a, bgr_px, in_px, t + 5, inimg);
+        float4 gr;
+        gr.x = gray_px(rr.a);
+        gr.y = gray_px(__funnelshift_r(rr.a, rr.b, 24));
+        gr.z = gray_px(__funnelshift_r(rr.b, rr.c, 16));
+        gr.w = gray_px(rr.c >> 8);
+        // GaussianBlur rows (sigma 1.1): columns g-2, g-1 from the left lane, g+4, g+5 from the right lane
+        float lz = __shfl_up_sync(SFE_FULL, gr.z, 1), lw = __shfl_up_sync(SFE_FULL, gr.w, 1);
+        float rx = __shfl_down_sync(SFE_FULL, gr.x, 1), ry = __shfl_down_sync(SFE_FULL, gr.y, 1);
+        if (ledge) { lz = gr.z; lw = gr.y; }   // columns -2, -1 mirror to 2, 1
+        if (redge) { rx = gr.z; ry = gr.y; }   // columns w, w+1 mirror to w-2, w-3
+        float4 hb;
+        hb.x = blur_row(lz, lw, gr.x, gr.y, gr.z, k0);
+        hb.y = blur_row(lw, gr.x, gr.y, gr.z, gr.w, k0);
+        hb.z = blur_row(gr.x, gr.y, gr.z, gr.w, rx, k0);
+        hb.w = blur_row(gr.y, gr.z, gr.w, rx, ry, k0);
+        hbw[u % 5] = hb;
+        // GaussianBlur columns: level-0 row q = t-2 from rows t-4..t
+        const float4 &h0 = hbw[(u + 1) % 5], &h1 = hbw[(u + 2) % 5], &h2 = hbw[(u + 3) % 5], &h3 = hbw[(u + 4) % 5], &h4 = hbw[u % 5];
+        row.x = blur_col(h0.x, h1.x, h2.x, h3.x, h4.x, k0);
+        row.y = blur_col(h0.y, h1.y, h2.y, h3.y, h4.y, k0);
+        row.z = blur_col(h0.z, h1.z, h2.z, h3.z, h4.z, k0);
+        row.w = blur_col(h0.w, h1.w, h2.w, h3.w, h4.w, k0);
+        if (useful && q >= r0 && q < q_hi) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
+      } else {
+        row = raw[u % 5].v;
+        load_row<false>(raw[u % 5], a, bgr_px, in_px, t + 5, inimg);
+      }
+
+      // pyrDown rows: pyrDown columns c0 = g/2 and c0+1 need input columns g-2..g+4
+      {
+        float lz = __shfl_up_sync(SFE_FULL, row.z, 1), lw = __shfl_up_sync(SFE_FULL, row.w, 1);
+        float rx = __shfl_down_sync(SFE_FULL, row.x, 1);
+        if (ledge) { lz = row.z; lw = row.y; }
+        if (redge) rx = row.z;
+        phw[u % 5] = make_float2(pd_h(lz, lw, row.x, row.y, row.z), pd_h(row.x, row.y, row.z, row.w, rx));
+      }
+      if (u % 2 == 0) {
+        // pyrDown columns: row i = (q-2)/2 from input rows q-4..q
+        const float2 &p0 = phw[(u + 1) % 5], &p1 = phw[(u + 2) % 5], &p2 = phw[(u + 3) % 5], &p3 = phw[(u + 4) % 5], &p4 = phw[u % 5];
+        const float pa = pd_v(p0.x, p1.x, p2.x, p3.x, p4.x), pb = pd_v(p0.y, p1.y, p2.y, p3.y, p4.y);
+        const int i = (q - 2) >> 1;
+        // GaussianBlur rows on the pyrDown row: columns c0-2, c0-1 from the left lane, c0+2, c0+3 from the right lane
+        float la = __shfl_up_sync(SFE_FULL, pa, 1), lb = __shfl_up_sync(SFE_FULL, pb, 1);
+        float ra = __shfl_down_sync(SFE_FULL, pa, 1), rb = __shfl_down_sync(SFE_FULL, pb, 1);
+        if (ledge) { la = ra; lb = pb; }   // columns -2, -1 mirror to 2, 1
+        if (redge) { ra = pa; rb = lb; }   // columns w1, w1+1 mirror to w1-2, w1-3
+        float2 bh = make_float2(blur_row(la, lb, pa, pb, ra, k1), blur_row(lb, pa, pb, ra, rb, k1));
+        const int v = (u / 2) % 5;
+        // below the image the pyrDown rows mirror about row h1-1: row h1 is row h1-2, row h1+1 is row h1-3
+        if (i == a.h1) bh = bhw[(v + 3) % 5];
+        if (i == a.h1 + 1) bh = bhw[(v + 1) % 5];
+        bhw[v] = bh;
+        const float2 &b0 = bhw[(v + 1) % 5], &b1 = bhw[(v + 2) % 5], &b2 = bhw[(v + 3) % 5], &b3 = bhw[(v + 4) % 5], &b4 = bhw[v];
+        const int j = i - 2;
+        if (useful && j >= j_lo && j < j_hi)
+          *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) =
+              make_float2(blur_col(b0.x, b1.x, b2.x, b3.x, b4.x, k1), blur_col(b0.y, b1.y, b2.y, b3.y, b4.y, k1));
+      }
+    }
+  }
+}
+
+int g_slots[2] = {0, 0};  // resident warps of the two instantiations on this device (one warp per CTA)
+
+template <bool FROM_BGR>
+int stream_slots() {
+  int& s = g_slots[FROM_BGR ? 0 : 1];
+  if (s == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_stream_kernel<FROM_BGR>, 32, 0);
+    s = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  return s;
+}
+
+// Row bands: enough units to fill the machine in ONE wave when the batch is small, one band per strip
+// otherwise (every band repeats ~15 rows of pipeline fill, so fewer and longer bands are cheaper).
+template <bool FROM_BGR>
+void plan_bands(StreamArgs& a, int count) {
+  const int slots = stream_slots<FROM_BGR>();
+  const int rows = 2 * a.h1;
+  int bands = slots / (count * a.strips);
+  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
+  if (bands < 1) bands = 1;
+  if (bands > max_bands) bands = max_bands;
+  int br = (rows + bands - 1) / bands;
+  br += br & 1;
+  a.band_rows = br;
+  a.bands = (rows + br - 1) / br;
+  a.nunits = count * a.strips * a.bands;
+}
+
+}  // namespace
+
+// Streams levels 0 and 1 of `count` frames (SFE_HESSIAN flavour) and then every deeper level the down
+// stage applies to.  Returns the number of levels built (>= 2) and adds the kernels launched to *launches,
+// or 0 when the geometry does not qualify (the caller falls back to the tiled kernels for all levels).
+int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first,
+                              int count, cudaStream_t s, int* launches) {
+  auto ok_level = [](int w, int h) { return w % 4 == 0 && w >= 16 && h >= 16; };
+  if (v.depth < 2 || !ok_level(v.w[0], v.h[0]) || ((uintptr_t)bgr & 3) || row_stride % 4 || frame_stride % 4) return 0;
+  int built = 0;
+  for (int l = 1; l < v.depth; ++l) {
+    if (!ok_level(v.w[l - 1], v.h[l - 1])) break;
+    StreamArgs a{};
+    a.w = v.w[l - 1]; a.h = v.h[l - 1]; a.w1 = v.w[l]; a.h1 = v.h[l];
+    a.first = first;
+    a.strips = (a.w + STRIP_USEFUL - 1) / STRIP_USEFUL;
+    a.out1 = v.base[0][l]; a.out1_fs = v.frame_stride[l]; a.out1_pitch = v.pitch[l];
+    a.blur1 = 1;  // sigma 0.8 (hessian.h:113)
+    if (l == 1) {
+      a.bgr = bgr; a.row_stride = row_stride; a.frame_stride = frame_stride;
+      a.out0 = v.base[0][0]; a.out0_fs = v.frame_stride[0]; a.out0_pitch = v.pitch[0];
+      a.blur0 = 0;  // sigma 1.1 (hessian.h:102)
+      plan_bands<true>(a, count);
+      pyr_stream_kernel<true><<<a.nunits, 32, 0, s>>>(a);
+    } else {
+      a.in = v.base[0][l - 1]; a.in_fs = v.frame_stride[l - 1]; a.in_pitch = v.pitch[l - 1];
+      plan_bands<false>(a, count);
+      pyr_stream_kernel<false><<<a.nunits, 32, 0, s>>>(a);
+    }
+    ++*launches;
+    built = l + 1;
+  }
+  return built;
+}
