@@ -18,6 +18,8 @@
 // neighbours from the mirrored pixels it already holds, and the last two level-1 rows take their
 // out-of-image pyrDown rows from the mirrored rows still in the window.
 // The arithmetic per pixel is pyr_math.cuh's, i.e. bit-identical to the tiled kernels and the oracle.
+#include <stdlib.h>
+
 #include "pyr_math.cuh"
 
 namespace {
@@ -57,28 +59,29 @@ __device__ __forceinline__ int reflect_row(int t, int h) {
   return min(max(t, 0), h - 1);  // the clamp only matters for ticks whose results are never stored
 }
 
-template <bool FROM_BGR>
-struct RawRow;
-template <>
-struct RawRow<true> { uint32_t a, b, c; };
-template <>
-struct RawRow<false> { float4 v; };
+// Input rows reach the lanes through a per-warp shared-memory ring filled by cp.async (LDGSTS) eight ticks
+// ahead: the copies are asynchronous and ordered only by commit/wait groups, so neither nvcc nor ptxas can
+// sink them next to their first use (plain or volatile loads were rescheduled five ticks late, exposing the
+// full DRAM latency on every tick -- profiles/README.md).  Each lane copies and later reads only its own
+// 12 (BGR) or 16 (float4) bytes, so no warp synchronisation is needed; out-of-image lanes copy zeros.
+constexpr int RING = 10, PREFETCH = 8;
 
 template <bool FROM_BGR>
-__device__ __forceinline__ void load_row(RawRow<FROM_BGR>& r, const StreamArgs& a, const uint8_t* bgr_px, const float* in_px,
-                                         int t, bool inimg) {
+__device__ __forceinline__ void issue_row(uint32_t slot_addr, const StreamArgs& a, const uint8_t* bgr_px, const float* in_px,
+                                          int t, int src_bytes) {
   const int ry = reflect_row(t, a.h);
   if constexpr (FROM_BGR) {
-    r.a = r.b = r.c = 0u;
-    if (inimg) {
-      const uint32_t* p = reinterpret_cast<const uint32_t*>(bgr_px + (size_t)ry * a.row_stride);
-      r.a = __ldg(p);
-      r.b = __ldg(p + 1);
-      r.c = __ldg(p + 2);
-    }
+    const uint8_t* p = bgr_px + (size_t)ry * a.row_stride;
+    asm volatile(
+        "cp.async.ca.shared.global [%0], [%1], 4, %2;\n\t"
+        "cp.async.ca.shared.global [%0+4], [%1+4], 4, %2;\n\t"
+        "cp.async.ca.shared.global [%0+8], [%1+8], 4, %2;\n\t"
+        "cp.async.commit_group;" ::"r"(slot_addr), "l"(p), "r"(src_bytes) : "memory");
   } else {
-    r.v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inimg) r.v = __ldg(reinterpret_cast<const float4*>(in_px + (size_t)ry * a.in_pitch));
+    const float* p = in_px + (size_t)ry * a.in_pitch;
+    asm volatile(
+        "cp.async.ca.shared.global [%0], [%1], 16, %2;\n\t"
+        "cp.async.commit_group;" ::"r"(slot_addr), "l"(p), "r"(src_bytes) : "memory");
   }
 }
 
@@ -117,9 +120,13 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   constexpr int LAG = FROM_BGR ? 2 : 0;
   const int t_begin = r0 - 8;  // even, so q is even exactly when the unrolled tick index is
   const int t_last = r1 + 4 + LAG;
-  RawRow<FROM_BGR> raw[5];
+  constexpr int LANE_BYTES = FROM_BGR ? 12 : 16;
+  __shared__ __align__(16) unsigned char ring[RING][32 * LANE_BYTES];
+  const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(&ring[0][lane * LANE_BYTES]);
+  const int src_bytes = inimg ? (FROM_BGR ? 4 : 16) : 0;
 #pragma unroll
-  for (int u = 0; u < 5; ++u) load_row<FROM_BGR>(raw[u], a, bgr_px, in_px, t_begin + u, inimg);
+  for (int u = 0; u < PREFETCH; ++u)
+    issue_row<FROM_BGR>(ring_addr + u * 32 * LANE_BYTES, a, bgr_px, in_px, t_begin + u, src_bytes);
 
   float4 hbw[5];   // FROM_BGR: horizontally blurred gray rows t-4..t
   float2 phw[5];   // horizontally pyrDown-filtered rows q-4..q
@@ -136,15 +143,19 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
     for (int u = 0; u < 10; ++u) {
       const int t = tb + u;
       const int q = t - LAG;
+      // row t has landed once at most PREFETCH-1 younger copy groups are still in flight; then refill the slot
+      // that was consumed two ticks ago with row t + PREFETCH
+      asm volatile("cp.async.wait_group %0;" ::"n"(PREFETCH - 1) : "memory");
+      issue_row<FROM_BGR>(ring_addr + ((u + PREFETCH) % RING) * 32 * LANE_BYTES, a, bgr_px, in_px, t + PREFETCH, src_bytes);
       float4 row;
       if constexpr (FROM_BGR) {
-        const RawRow<true> rr = raw[u % 5];
-        load_row<true>(raw[u % 5], a, bgr_px, in_px, t + 5, inimg);
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(&ring[u % RING][lane * LANE_BYTES]);
+        const uint32_t ra_ = rr[0], rb_ = rr[1], rc_ = rr[2];
         float4 gr;
-        gr.x = gray_px(rr.a);
-        gr.y = gray_px(__funnelshift_r(rr.a, rr.b, 24));
-        gr.z = gray_px(__funnelshift_r(rr.b, rr.c, 16));
-        gr.w = gray_px(rr.c >> 8);
+        gr.x = gray_px(ra_);
+        gr.y = gray_px(__funnelshift_r(ra_, rb_, 24));
+        gr.z = gray_px(__funnelshift_r(rb_, rc_, 16));
+        gr.w = gray_px(rc_ >> 8);
         // GaussianBlur rows (sigma 1.1): columns g-2, g-1 from the left lane, g+4, g+5 from the right lane
         float lz = __shfl_up_sync(SFE_FULL, gr.z, 1), lw = __shfl_up_sync(SFE_FULL, gr.w, 1);
         float rx = __shfl_down_sync(SFE_FULL, gr.x, 1), ry = __shfl_down_sync(SFE_FULL, gr.y, 1);
@@ -164,8 +175,7 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         row.w = blur_col(h0.w, h1.w, h2.w, h3.w, h4.w, k0);
         if (useful && q >= r0 && q < q_hi) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
       } else {
-        row = raw[u % 5].v;
-        load_row<false>(raw[u % 5], a, bgr_px, in_px, t + 5, inimg);
+        row = *reinterpret_cast<const float4*>(&ring[u % RING][lane * LANE_BYTES]);
       }
 
       // pyrDown rows: pyrDown columns c0 = g/2 and c0+1 need input columns g-2..g+4
@@ -217,13 +227,16 @@ int stream_slots() {
   return s;
 }
 
-// Row bands: enough units to fill the machine in ONE wave when the batch is small, one band per strip
-// otherwise (every band repeats ~15 rows of pipeline fill, so fewer and longer bands are cheaper).
+// Row bands.  Every band repeats ~15 rows of pipeline fill, so long bands are cheaper per pixel, but the
+// kernel needs enough warps to keep the issue slots busy: measured on B200 (profiles/README.md) about 1.3x
+// the resident warp slots is the sweet spot (256 VGA frames: 3 bands of 160 rows beat 2 and 4).
 template <bool FROM_BGR>
 void plan_bands(StreamArgs& a, int count) {
   const int slots = stream_slots<FROM_BGR>();
   const int rows = 2 * a.h1;
-  int bands = slots / (count * a.strips);
+  int bands = (int)(1.3 * slots / ((double)count * a.strips) + 0.5);
+  static const int forced = getenv("SFE_PYR_BANDS") ? atoi(getenv("SFE_PYR_BANDS")) : 0;  // experiments
+  if (forced > 0) bands = forced;
   const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
   if (bands < 1) bands = 1;
   if (bands > max_bands) bands = max_bands;
