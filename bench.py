@@ -182,17 +182,25 @@ def run_gpu(args):
     accepted = int(trk_out["accepted"].sum().item())
     passed = int(ham_out[2].sum().item())
 
-    # ---- end to end through the host-pointer C ABI: pinned host inputs, results back on the host
+    # ---- end to end through the host-pointer C ABI (the call a user makes): pinned host inputs, results back
+    # in host memory.  sfe_replay_pairs pipelines the step in chunks (upload | pyramids + tracking | download);
+    # the descriptor matching of the step is enqueued first with sfe_match_hamming256_async and drains with it.
     hA, hB = A.cpu().pin_memory(), Bf.cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
     fe.set_stream(None)
+    h_pts = fe.pinned((n, 2), np.float32)
+    h_pts[...] = pts
+    h_q, h_t = fe.pinned(q.shape, np.uint32), fe.pinned(t.shape, np.uint32)
+    h_q[...] = q
+    h_t[...] = t
+    h_trk = dict(to_xy=fe.pinned((n, 2), np.float32), back_xy=fe.pinned((n, 2), np.float32), status_fwd=fe.pinned((n,), np.int32),
+                 status_bwd=fe.pinned((n,), np.int32), accepted=fe.pinned((n,), np.uint8), steps=fe.pinned((n,), np.int32))
+    h_ham = (fe.pinned((n, 2), np.int32), fe.pinned((n, 2), np.int32), fe.pinned((n,), np.uint8))
 
     def step_e2e():
-        pa.build(hA)
-        pb.build(hB)
-        r = fe.track_fb(pa, pb, pts, pts, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT)
-        m = fe.match_hamming256(q, t, *RATIO, batch=B)
-        return r, m
+        fe.match_hamming256_async(h_q, h_t, h_ham, *RATIO, batch=B)
+        r = fe.replay_pairs(hA, hB, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+        return r, h_ham
 
     step_e2e()
     barrier()
@@ -204,6 +212,7 @@ def run_gpu(args):
     h2d = 2 * B * H * W * 3 + n * 16 + 2 * n * 32
     d2h = n * (8 + 8 + 4 + 4 + 1 + 4) + n * (8 + 8 + 1)
     assert np.array_equal(r["accepted"], trk_out["accepted"].cpu().numpy()), "host and device paths disagree"
+    assert np.array_equal(m[0], ham_out[0].cpu().numpy()), "host and device matching paths disagree"
 
     # ---- max over ranks
     tt = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)

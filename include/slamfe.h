@@ -185,6 +185,31 @@ int sfe_match_hamming256_dev(sfe_ctx* ctx, const uint32_t* q, int nq, const uint
                              int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
                              int32_t* dist, uint8_t* pass);
 
+/* As sfe_match_hamming256, but only ENQUEUES the uploads, the kernels and the downloads on the
+ * context's stream: the result buffers are valid after sfe_sync().  The host buffers must stay
+ * alive until then (pinned memory from sfe_host_alloc makes the copies truly asynchronous); one
+ * asynchronous call may be outstanding per context. */
+int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt,
+                               int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
+                               int32_t* dist, uint8_t* pass);
+
+/* ---- batched replay of independent frame pairs ------------------------------------------ */
+
+/* The host-side batching/stream layer: what Matcher::Track does per frame -- MakePyramid
+ * (matcher.cpp:317) and the FindMatches tracking loop (matcher.cpp:208-271 -> :173-206) -- for
+ * `npairs` independent (from, to) frame pairs of a replayed sequence (BASELINE config 4), host
+ * buffers in and out.  The pairs are processed in chunks of `chunk_pairs` (<= 0: automatic) on a
+ * three-stream pipeline (upload of chunk k+1 | pyramids + tracking of chunk k | download of chunk
+ * k-1), so with pinned host buffers the PCIe transfers hide behind the kernels.
+ *   from_bgr, to_bgr  npairs frames each, 8-bit BGR, row_stride / frame_stride in bytes
+ *   feature arrays    npairs * n_per_pair entries, pair-major, semantics of sfe_track_fb
+ * Returns after all results are in the caller's buffers. */
+int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
+                     const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+                     const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                     int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ EXPORTS = [
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
+    "sfe_match_hamming256_async", "sfe_replay_pairs",
 ]
 
 
@@ -109,6 +110,9 @@ def lib():
     ham = [vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.sfe_match_hamming256.argtypes = ham
     L.sfe_match_hamming256_dev.argtypes = ham
+    L.sfe_match_hamming256_async.argtypes = ham
+    L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
+                                   vp, vp, i32]
     _lib = L
     return L
 
@@ -146,6 +150,9 @@ class FrontEnd:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.L.sfe_host_free(self.h, p)
+            self._pinned = []
             self.L.sfe_destroy(self.h)
             self.h = None
 
@@ -299,7 +306,57 @@ class FrontEnd:
                                          _ptr(st), _ptr(sad), C.addressof(pos)))
         return dict(to_xy=to_xy, status=st, best_sad=sad, positions=pos.value)
 
+    # ---- batched replay of independent frame pairs (host buffers, chunk-pipelined; include/slamfe.h)
+    def replay_pairs(self, frames_from, frames_to, from_xy, seed_xy, depth, levels=3, thr=0.001, maxit=10, fb_max=0.3,
+                     n_per_pair=None, chunk_pairs=0, out=None, want_steps=True):
+        """frames_*: (npairs,H,W,3) uint8 host arrays (numpy or CPU torch tensors, ideally pinned);
+        from_xy/seed_xy: (npairs*n_per_pair, 2) float32 host arrays.  seed_xy is NOT modified."""
+        npairs, H, W, ch = frames_from.shape
+        assert ch == 3 and tuple(frames_to.shape) == (npairs, H, W, 3)
+        from_xy = from_xy if _is_torch(from_xy) else _np(from_xy, np.float32).reshape(-1, 2)
+        n = from_xy.shape[0]
+        npp = n // max(npairs, 1) if n_per_pair is None else int(n_per_pair)
+        assert npp * npairs == n
+        if out is None:
+            out = dict(to_xy=np.empty((n, 2), np.float32), back_xy=np.empty((n, 2), np.float32), status_fwd=np.empty(n, np.int32),
+                       status_bwd=np.empty(n, np.int32), accepted=np.empty(n, np.uint8),
+                       steps=np.empty(n, np.int32) if want_steps else None)
+        to_xy = out["to_xy"]
+        if _is_torch(to_xy):
+            to_xy.copy_(seed_xy if _is_torch(seed_xy) else __import__("torch").from_numpy(np.asarray(seed_xy, np.float32)))
+        else:
+            to_xy[...] = np.asarray(seed_xy, np.float32).reshape(-1, 2)
+        lv_arr = None
+        if levels is not None and not np.isscalar(levels):
+            lv_arr = _np(levels, np.int32)
+        for a in (frames_from, frames_to):
+            assert (a.is_contiguous() if _is_torch(a) else a.flags.c_contiguous) and not (_is_torch(a) and a.is_cuda)
+        self._chk(self.L.sfe_replay_pairs(self.h, W, H, depth, npairs, _ptr(frames_from), _ptr(frames_to), 3 * W, 3 * W * H, max(npp, 1),
+                                          _ptr(from_xy), _ptr(to_xy), _ptr(lv_arr), int(levels) if lv_arr is None else 3, thr,
+                                          maxit, fb_max, _ptr(out["back_xy"]), _ptr(out["status_fwd"]), _ptr(out["status_bwd"]),
+                                          _ptr(out["accepted"]), _ptr(out.get("steps")), int(chunk_pairs)))
+        return out
+
+    def pinned(self, shape, dtype):
+        """A page-locked host array (sfe_host_alloc): lets the host-pointer entry points copy asynchronously."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._chk(self.L.sfe_host_alloc(self.h, max(nbytes, 1), C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
+
     # ---- P4
+    def match_hamming256_async(self, q, t, out, ratio_num=4, ratio_den=5, max_dist=256, batch=1):
+        """Host arrays (pinned for real asynchrony); only enqueues -- call sync() before reading `out`."""
+        nq, nt = q.shape[0] // batch, t.shape[0] // batch
+        self._chk(self.L.sfe_match_hamming256_async(self.h, _ptr(q), nq, _ptr(t), nt, batch, ratio_num, ratio_den, max_dist,
+                                                    _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
     def match_hamming256(self, q, t, ratio_num=4, ratio_den=5, max_dist=256, batch=1, out=None):
         """q: (batch*nq, 8) uint32, t: (batch*nt, 8) uint32 (numpy -> host path, CUDA tensors -> device path)."""
         dev = _is_torch(q) and q.is_cuda

@@ -8,34 +8,7 @@
 
 #include <new>
 
-#include "sfe_common.cuh"
-
-struct sfe_ctx {
-  int device;
-  cudaStream_t own_stream;
-  cudaStream_t stream;
-  float* d_mask;
-  int* d_counter;  // work-queue head of the persistent tracking kernels
-  int num_sms;
-  float h_mask[SFE_PLEN];
-  // grow-on-demand device scratch for the host-pointer entry points
-  void* scratch;
-  size_t scratch_cap;
-  void* ham_ws;
-  size_t ham_cap;
-  int64_t launches;
-  char err[512];
-};
-
-struct sfe_pyr {
-  sfe_ctx* ctx;
-  int flavor;
-  int planes;
-  PyrView view;
-  float* storage;
-  size_t storage_floats;
-  int64_t bytes_per_frame;
-};
+#include "ctx.cuh"
 
 namespace {
 
@@ -204,8 +177,10 @@ void sfe_destroy(sfe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  sfe_replay_release(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
+  if (ctx->ham_io) cudaFree(ctx->ham_io);
   cudaFree(ctx->d_mask);
   cudaFree(ctx->d_counter);
   cudaStreamDestroy(ctx->own_stream);
@@ -607,6 +582,40 @@ int sfe_match_hamming256(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t
   CU(cudaMemcpyAsync(dist, d_d, ob, cudaMemcpyDeviceToHost, s));
   if (pass) CU(cudaMemcpyAsync(pass, d_p, (size_t)nq * batch, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+
+int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int batch,
+                               int ratio_num, int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass) {
+  if (!ctx || nq < 0 || nt < 0 || batch < 1 || !idx || !dist || (nq && !q) || (nt && !t))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad hamming arguments");
+  if (nq == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  const size_t qb = 32 * (size_t)nq * batch, tb = 32 * (size_t)nt * batch, ob = 8 * (size_t)nq * batch;
+  const size_t need = padded(qb) + padded(tb) + 2 * padded(ob) + padded((size_t)nq * batch);
+  if (need > ctx->ham_io_cap) {
+    CU(cudaStreamSynchronize(ctx->stream));  // a previous asynchronous call may still be using the old buffers
+    if (ctx->ham_io) CU(cudaFree(ctx->ham_io));
+    ctx->ham_io = nullptr;
+    ctx->ham_io_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->ham_io, need + need / 4);
+    if (e != cudaSuccess) return fail(ctx, SFE_ERR_NOMEM, "cudaMalloc(hamming io): %s", cudaGetErrorString(e));
+    ctx->ham_io_cap = need + need / 4;
+  }
+  Carver c{(char*)ctx->ham_io, 0};
+  uint32_t* d_q = c.take<uint32_t>(8 * (size_t)nq * batch);
+  uint32_t* d_t = c.take<uint32_t>(8 * (size_t)nt * batch);
+  int32_t* d_i = c.take<int32_t>(2 * (size_t)nq * batch);
+  int32_t* d_d = c.take<int32_t>(2 * (size_t)nq * batch);
+  uint8_t* d_p = c.take<uint8_t>((size_t)nq * batch);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_q, q, qb, cudaMemcpyHostToDevice, s));
+  if (nt) CU(cudaMemcpyAsync(d_t, t, tb, cudaMemcpyHostToDevice, s));
+  int rc = sfe_match_hamming256_dev(ctx, d_q, nq, d_t, nt, batch, ratio_num, ratio_den, max_dist, d_i, d_d, pass ? d_p : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(idx, d_i, ob, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(dist, d_d, ob, cudaMemcpyDeviceToHost, s));
+  if (pass) CU(cudaMemcpyAsync(pass, d_p, (size_t)nq * batch, cudaMemcpyDeviceToHost, s));
   return SFE_SUCCESS;
 }
 

@@ -1,0 +1,38 @@
+// ctx.cuh -- the objects behind the opaque handles of include/slamfe.h (shared by capi.cu and replay.cu).
+#pragma once
+#include "sfe_common.cuh"
+
+struct sfe_replay;  // replay.cu: the chunk pipeline's streams, events and staging buffers
+
+struct sfe_ctx {
+  int device;
+  cudaStream_t own_stream;
+  cudaStream_t stream;
+  float* d_mask;
+  int* d_counter;  // work-queue head of the persistent tracking kernels
+  int num_sms;
+  float h_mask[SFE_PLEN];
+  // grow-on-demand device scratch for the host-pointer entry points
+  void* scratch;
+  size_t scratch_cap;
+  void* ham_ws;
+  size_t ham_cap;
+  void* ham_io;   // device buffers of sfe_match_hamming256_async (must outlive the call, so not the shared scratch)
+  size_t ham_io_cap;
+  int64_t launches;
+  sfe_replay* replay;  // lazily created by sfe_replay_pairs
+  char err[512];
+};
+
+struct sfe_pyr {
+  sfe_ctx* ctx;
+  int flavor;
+  int planes;
+  PyrView view;
+  float* storage;
+  size_t storage_floats;
+  int64_t bytes_per_frame;
+};
+
+
+void sfe_replay_release(sfe_ctx* ctx);  // replay.cu

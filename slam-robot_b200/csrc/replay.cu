@@ -1,0 +1,214 @@
+// replay.cu -- sfe_replay_pairs: the host-side batching/stream layer for replaying independent frame
+// pairs (BASELINE config 4; the per-frame body is matcher.cpp:317 MakePyramid + :208-271 FindMatches).
+//
+// Host buffers in, host buffers out.  The pairs are cut into chunks; three CUDA streams form a pipeline
+//   copy stream     H2D of the BGR frames of chunk k+1 (double-buffered device staging)
+//   compute stream  MakePyramid of both frames + forward/backward tracking of chunk k (the context's stream)
+//   output stream   D2H of the results of chunk k-1
+// ordered by events only, so with pinned host buffers (sfe_host_alloc) the PCIe traffic of a step hides
+// behind its kernels.  Staging buffers, pyramids and events are cached in the context between calls.
+#include <new>
+#include <stdio.h>
+#include <string.h>
+
+#include "ctx.cuh"
+
+struct sfe_replay {
+  cudaStream_t copy_stream, out_stream;
+  cudaEvent_t copied[2], consumed[2], tracked[2], drained;
+  int w, h, depth, chunk;  // geometry the frame buffers / pyramids were built for
+  uint8_t* d_frames[2];    // per buffer: `chunk` from-frames followed by `chunk` to-frames
+  sfe_pyr* pyr_from[2];
+  sfe_pyr* pyr_to[2];
+  size_t n_cap;            // feature capacity of the arrays below
+  float *d_from, *d_to, *d_back;
+  int32_t *d_lv, *d_s1, *d_s2, *d_steps;
+  uint8_t* d_acc;
+};
+
+namespace {
+
+int rfail(sfe_ctx* c, int code, const char* what, cudaError_t e) {
+  snprintf(c->err, sizeof(c->err), "sfe_replay_pairs: %s%s%s", what, e != cudaSuccess ? ": " : "",
+           e != cudaSuccess ? cudaGetErrorString(e) : "");
+  return code;
+}
+
+#define RCU(call)                                                        \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) return rfail(ctx, SFE_ERR_CUDA, #call, e_);   \
+  } while (0)
+
+void free_geometry(sfe_replay* r) {
+  for (int b = 0; b < 2; ++b) {
+    if (r->d_frames[b]) cudaFree(r->d_frames[b]);
+    if (r->pyr_from[b]) sfe_pyr_destroy(r->pyr_from[b]);
+    if (r->pyr_to[b]) sfe_pyr_destroy(r->pyr_to[b]);
+    r->d_frames[b] = nullptr;
+    r->pyr_from[b] = r->pyr_to[b] = nullptr;
+  }
+  r->w = r->h = r->depth = r->chunk = 0;
+}
+
+void free_features(sfe_replay* r) {
+  void* p[] = {r->d_from, r->d_to, r->d_back, r->d_lv, r->d_s1, r->d_s2, r->d_steps, r->d_acc};
+  for (void* q : p)
+    if (q) cudaFree(q);
+  r->d_from = r->d_to = r->d_back = nullptr;
+  r->d_lv = r->d_s1 = r->d_s2 = r->d_steps = nullptr;
+  r->d_acc = nullptr;
+  r->n_cap = 0;
+}
+
+int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
+  sfe_replay* r = ctx->replay;
+  if (!r) {
+    r = new (std::nothrow) sfe_replay();
+    if (!r) return rfail(ctx, SFE_ERR_NOMEM, "out of host memory", cudaSuccess);
+    memset(r, 0, sizeof(*r));
+    ctx->replay = r;
+    RCU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    RCU(cudaStreamCreateWithFlags(&r->out_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      RCU(cudaEventCreateWithFlags(&r->copied[b], cudaEventDisableTiming));
+      RCU(cudaEventCreateWithFlags(&r->consumed[b], cudaEventDisableTiming));
+      RCU(cudaEventCreateWithFlags(&r->tracked[b], cudaEventDisableTiming));
+    }
+    RCU(cudaEventCreateWithFlags(&r->drained, cudaEventDisableTiming));
+  }
+  if (r->w != w || r->h != h || r->depth != depth || r->chunk != chunk) {
+    RCU(cudaStreamSynchronize(ctx->stream));
+    free_geometry(r);
+    for (int b = 0; b < 2; ++b) {
+      cudaError_t e = cudaMalloc(&r->d_frames[b], (size_t)2 * chunk * 3 * w * h);
+      if (e != cudaSuccess) return rfail(ctx, SFE_ERR_NOMEM, "cudaMalloc(frame staging)", e);
+      int rc = sfe_pyr_create(ctx, w, h, depth, SFE_HESSIAN, chunk, &r->pyr_from[b]);
+      if (!rc) rc = sfe_pyr_create(ctx, w, h, depth, SFE_HESSIAN, chunk, &r->pyr_to[b]);
+      if (rc) return rc;
+    }
+    r->w = w; r->h = h; r->depth = depth; r->chunk = chunk;
+  }
+  if (n > r->n_cap) {
+    RCU(cudaStreamSynchronize(ctx->stream));
+    free_features(r);
+    const size_t cap = n + n / 4 + 1024;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_from, 8 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_to, 8 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_back, 8 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_lv, 4 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_s1, 4 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_s2, 4 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_steps, 4 * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_acc, cap);
+    if (e != cudaSuccess) return rfail(ctx, SFE_ERR_NOMEM, "cudaMalloc(feature arrays)", e);
+    r->n_cap = cap;
+  }
+  return SFE_SUCCESS;
+}
+
+int upload_frames(sfe_ctx* ctx, uint8_t* dst, const uint8_t* src, int w, int h, size_t row_stride, size_t frame_stride,
+                  int count, cudaStream_t s) {
+  const size_t dense_row = (size_t)3 * w, dense_frame = dense_row * h;
+  if (row_stride == dense_row && (frame_stride == dense_frame || count == 1)) {
+    RCU(cudaMemcpyAsync(dst, src, dense_frame * count, cudaMemcpyHostToDevice, s));
+  } else {
+    for (int f = 0; f < count; ++f)
+      RCU(cudaMemcpy2DAsync(dst + f * dense_frame, dense_row, src + f * frame_stride, row_stride, dense_row, h,
+                            cudaMemcpyHostToDevice, s));
+  }
+  return SFE_SUCCESS;
+}
+
+}  // namespace
+
+void sfe_replay_release(sfe_ctx* ctx) {
+  sfe_replay* r = ctx->replay;
+  if (!r) return;
+  free_geometry(r);
+  free_features(r);
+  for (int b = 0; b < 2; ++b) {
+    if (r->copied[b]) cudaEventDestroy(r->copied[b]);
+    if (r->consumed[b]) cudaEventDestroy(r->consumed[b]);
+    if (r->tracked[b]) cudaEventDestroy(r->tracked[b]);
+  }
+  if (r->drained) cudaEventDestroy(r->drained);
+  if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+  if (r->out_stream) cudaStreamDestroy(r->out_stream);
+  delete r;
+  ctx->replay = nullptr;
+}
+
+extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
+                                const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+                                const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
+                                int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                                uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (npairs == 0) return SFE_SUCCESS;
+  if (w < 1 || h < 1 || depth < 1 || depth > SFE_MAX_LEVELS || npairs < 0 || n_per_pair < 1 || !from_bgr || !to_bgr ||
+      !from_xy || !to_xy || default_levels < 1 || maxit < 0 || row_stride < (size_t)3 * w)
+    return rfail(ctx, SFE_ERR_INVALID, "bad arguments", cudaSuccess);
+  RCU(cudaSetDevice(ctx->device));
+  // chunk size: default = an eighth of the batch (the first chunk's upload and the last chunk's download are
+  // the only exposed transfers), at least 8 pairs so that the kernels still fill the GPU
+  int chunk = chunk_pairs > 0 ? chunk_pairs : (npairs + 7) / 8;
+  if (chunk_pairs <= 0 && chunk < 8) chunk = 8;
+  if (chunk > npairs) chunk = npairs;
+  const size_t n = (size_t)npairs * n_per_pair;
+  int rc = ensure(ctx, w, h, depth, chunk, n);
+  if (rc) return rc;
+  sfe_replay* r = ctx->replay;
+  cudaStream_t cs = ctx->stream, xs = r->copy_stream, os = r->out_stream;
+
+  // the feature lists are small: upload them in one piece ahead of the pipeline
+  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs));
+  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs));
+  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs));
+  // the copy and output streams must not run ahead of whatever the caller queued on the context's stream
+  // before this call, nor reuse the staging buffers of a previous call that is still in flight
+  RCU(cudaEventRecord(r->drained, cs));
+  RCU(cudaStreamWaitEvent(xs, r->drained, 0));
+  RCU(cudaStreamWaitEvent(os, r->drained, 0));
+
+  const size_t dense_frame = (size_t)3 * w * h;
+  const int nchunks = (npairs + chunk - 1) / chunk;
+  for (int k = 0; k < nchunks; ++k) {
+    const int b = k & 1, p0 = k * chunk, c = npairs - p0 < chunk ? npairs - p0 : chunk;
+    // ---- copy stream: frames of chunk k into staging buffer b (free once chunk k-2's pyramids are built)
+    if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
+    rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride, c, xs);
+    if (!rc)
+      rc = upload_frames(ctx, r->d_frames[b] + (size_t)chunk * dense_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
+                         row_stride, frame_stride, c, xs);
+    if (rc) return rc;
+    RCU(cudaEventRecord(r->copied[b], xs));
+    // ---- compute stream: both pyramids, then forward/backward tracking of the chunk's features
+    RCU(cudaStreamWaitEvent(cs, r->copied[b], 0));
+    rc = sfe_pyr_build_dev(ctx, r->pyr_from[b], r->d_frames[b], (size_t)3 * w, dense_frame, 0, c);
+    if (!rc) rc = sfe_pyr_build_dev(ctx, r->pyr_to[b], r->d_frames[b] + (size_t)chunk * dense_frame, (size_t)3 * w, dense_frame, 0, c);
+    if (rc) return rc;
+    RCU(cudaEventRecord(r->consumed[b], cs));
+    const size_t f0 = (size_t)p0 * n_per_pair;
+    const int nf = c * n_per_pair;
+    rc = sfe_track_fb_dev(ctx, r->pyr_from[b], 0, r->pyr_to[b], 0, nf, n_per_pair, r->d_from + 2 * f0, r->d_to + 2 * f0,
+                          levels ? r->d_lv + f0 : nullptr, default_levels, thr, maxit, fb_max, r->d_back + 2 * f0,
+                          r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0);
+    if (rc) return rc;
+    RCU(cudaEventRecord(r->tracked[b], cs));
+    // ---- output stream: results of chunk k back to the caller's buffers
+    RCU(cudaStreamWaitEvent(os, r->tracked[b], 0));
+    RCU(cudaMemcpyAsync(to_xy + 2 * f0, r->d_to + 2 * f0, 8 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (back_xy) RCU(cudaMemcpyAsync(back_xy + 2 * f0, r->d_back + 2 * f0, 8 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (status_fwd) RCU(cudaMemcpyAsync(status_fwd + f0, r->d_s1 + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (status_bwd) RCU(cudaMemcpyAsync(status_bwd + f0, r->d_s2 + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (accepted) RCU(cudaMemcpyAsync(accepted + f0, r->d_acc + f0, (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (steps) RCU(cudaMemcpyAsync(steps + f0, r->d_steps + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+  }
+  // join: the context's stream is complete only when the last download is
+  RCU(cudaEventRecord(r->drained, os));
+  RCU(cudaStreamWaitEvent(cs, r->drained, 0));
+  RCU(cudaStreamSynchronize(cs));
+  return SFE_SUCCESS;
+}

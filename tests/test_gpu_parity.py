@@ -162,6 +162,39 @@ def test_track_fb_batched_pairs(fe, po, synth):
         assert_bits_equal(g["back_xy"][sl], o["back_xy"], "pair %d back_xy" % p)
 
 
+@pytest.mark.parametrize("chunk", [2, 0, 5])
+def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
+    """sfe_replay_pairs (host buffers, chunk-pipelined over three streams): 5 pairs in chunks of 2 (ragged last
+    chunk), automatic chunking and a single chunk -- every pair equals the single-pair oracle run bit for bit."""
+    H, W = 240, 320
+    npairs, npp = 5, 130
+    A, B = synth.make_pairs(33, npairs, H, W)
+    A, B = A.numpy(), B.numpy()
+    pts = np.concatenate([_features(synth, npp, H, W, seed=40 + p) for p in range(npairs)])
+    lv = np.where(np.arange(npairs * npp) % 4 == 0, 2, 4).astype(np.int32)
+    g = fe.replay_pairs(A, B, pts, pts, depth=4, levels=lv, n_per_pair=npp, chunk_pairs=chunk)
+    for p in range(npairs):
+        oa, ob = po.Pyramid(A[p], 4), po.Pyramid(B[p], 4)
+        sl = slice(p * npp, (p + 1) * npp)
+        o = po.hes_track_fb(oa, ob, pts[sl], pts[sl], lv[sl])
+        for k in ("status_fwd", "status_bwd", "accepted"):
+            assert np.array_equal(g[k][sl], o[k]), (p, k)
+        assert_bits_equal(g["to_xy"][sl], o["to_xy"], "pair %d to_xy" % p)
+        assert_bits_equal(g["back_xy"][sl], o["back_xy"], "pair %d back_xy" % p)
+    # pinned buffers + the asynchronous matcher queued ahead of the replay (the bench's e2e step)
+    hq = synth.make_descriptors(5, 700, 0.2)
+    ht = synth.make_descriptors(6, 900, 0.1)
+    out = (np.empty((700, 2), np.int32), np.empty((700, 2), np.int32), np.empty(700, np.uint8))
+    fe.match_hamming256_async(hq, ht, out, 4, 5, 80)
+    pA, pB = fe.pinned(A.shape, np.uint8), fe.pinned(B.shape, np.uint8)
+    pA[...] = A
+    pB[...] = B
+    g2 = fe.replay_pairs(pA, pB, pts, pts, depth=4, levels=lv, n_per_pair=npp, chunk_pairs=chunk)
+    assert_bits_equal(g2["to_xy"], g["to_xy"], "pinned replay")
+    oi, od, oo = po.hamming256_top2(hq, ht, 4, 5, 80)
+    assert np.array_equal(out[0], oi) and np.array_equal(out[1], od) and np.array_equal(out[2], oo)
+
+
 def test_track_fb_empty_and_errors(fe, sfe, pair640):
     A, _ = pair640
     ga = fe.make_pyramid(A, 3)
