@@ -43,52 +43,73 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a
+    thread every 2 ms (the timed region is ~100 ms; nvidia-smi -lms cannot sample that fast), nvidia-smi as a
+    fallback when NVML cannot be loaded."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.idx = gpu_index
+        self.sm, self.mask, self.power = [], 0, []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.sm_max = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = threading.Thread(target=self._run_nvml if self.nvml else self._run_smi, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run_nvml(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        bits = [0x8, 0x40, 0x20, 0x4]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout
+                r = [c.strip() for c in out.strip().split(",")]
+                self.sm.append(float(r[0]))
+                self.sm_max = float(r[1])
+                for bit, v in zip(bits, r[2:6]):
+                    if v.lower().startswith("active"):
+                        self.mask |= bit
+            except Exception:
+                time.sleep(0.05)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=6)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "source": "nvml" if self.nvml else "nvidia-smi",
+                "reasons": reasons}
 
 
 def make_inputs(torch, synth, batch, device, seed):
@@ -158,12 +179,14 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-        barrier()
+        # clocks / throttle reasons are sampled from the first warm-up step through the timed region and an
+        # untimed tail of identical steps (the timed region alone, ~0.1 s, is shorter than a few NVML queries)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step()
+        barrier()
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
         l0 = fe.launch_count()
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -172,8 +195,16 @@ def run_gpu(args):
             step(evs[k])
         t_end.record(stream)
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
         launches = fe.launch_count() - l0
+        if rank == 0:
+            t_tail = time.perf_counter()
+            while time.perf_counter() - t_tail < 0.5:
+                step()
+                torch.cuda.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks["window"] = "warm-up + timed region + 0.5 s untimed tail of identical steps"
+        barrier()
     ms_total = t_start.elapsed_time(t_end)
     ms_pyr = sum(e[0].elapsed_time(e[1]) for e in evs)
     ms_trk = sum(e[1].elapsed_time(e[2]) for e in evs)
@@ -199,7 +230,8 @@ def run_gpu(args):
 
     def step_e2e():
         fe.match_hamming256_async(h_q, h_t, h_ham, *RATIO, batch=B)
-        r = fe.replay_pairs(hA, hB, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+        r = fe.replay_pairs(hA, hB, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk,
+                            chunk_pairs=int(os.environ.get("SFE_BENCH_CHUNK", "0")))
         return r, h_ham
 
     step_e2e()
@@ -253,7 +285,7 @@ def run_gpu(args):
                          "bilinear_samples_per_sec": newton * 6 * 169 / args.steps / 1.0 / (trk_ms * 1e-3) if False else
                          (newton * 6 * 169) / (trk_ms * 1e-3)},
             # the HBM-streaming kernels of the path
-            "roofline_pyramid": {"kernel": "pyr_l0_kernel + pyr_down_kernel", "bound": "hbm",
+            "roofline_pyramid": {"kernel": "pyr_stream_kernel<bgr> (levels 0+1 fused) + pyr_stream_kernel<down> x2", "bound": "hbm",
                                  "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": None,
                                  "share_of_step": pyr_ms / ms_step},

@@ -44,6 +44,8 @@ struct WarpScratch {
   float zero[TS + 2];                // must directly follow tile
   float pad[32 - (TS + 2) % 32];
   float v[6 * SFE_SLOTS * 32];       // general route: patch value of shift s, slot k, lane l at [(s*6+k)*32 + l]
+  float T[SFE_SLOTS * 32];           // template patch and its effective mask, slot k of lane l at [k*32 + l]
+  float mkT[SFE_SLOTS * 32];
 };
 
 // x variants live in lanes 0..2 (p, p-h, p+h), y variants in lanes 4..6; BruteHessian's shifts
@@ -187,9 +189,11 @@ __device__ __forceinline__ void finite_differences(float sc, int lane, float (&d
   d[4] = __shfl_sync(SFE_FULL, rf, 3);
 }
 
+// Statistics of the template patch (hessian.h:32-40).  The patch itself and its effective mask (the mask
+// weight, 0 where the template pixel is exactly 0, hessian.h:134) are parked in WarpScratch::T / mkT: they
+// are needed only in the score loop, and keeping them out of the registers while the 36 candidate values
+// are live is worth 3 % (profiles/README.md).
 struct Tmpl {
-  float T[SFE_SLOTS];    // the template patch (hessian.h:32-40)
-  float mkT[SFE_SLOTS];  // mask weight, 0 where the template pixel is exactly 0 (hessian.h:134)
   float mean, sumsq;
 };
 
@@ -232,9 +236,9 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
       const float v = S.v[k * 32 + lane];
       sm = sm + v;
       sq = fmaf(v, v, sq);
-      t.T[k] = v;
       const float m = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
-      t.mkT[k] = v == 0.f ? 0.f : m;
+      S.T[k * 32 + lane] = v;
+      S.mkT[k * 32 + lane] = v == 0.f ? 0.f : m;
     }
     const float red = packed_reduce2(sm, sq, lane) / (float)SFE_PLEN;
     t.mean = __shfl_sync(SFE_FULL, red, 0);
@@ -302,6 +306,12 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   const float beta_l = t.mean - alpha_l * mean;
   float part[8];
   part[6] = part[7] = 0.f;
+  float T[SFE_SLOTS], mkT[SFE_SLOTS];  // parked in shared memory while the patch values occupy the registers
+#pragma unroll
+  for (int k = 0; k < SFE_SLOTS; ++k) {
+    T[k] = S.T[k * 32 + lane];
+    mkT[k] = S.mkT[k * 32 + lane];
+  }
   if (!zeros) {
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -309,9 +319,9 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139; template zeros are folded into mkT
-        float diff = fmaf(-v[s][k], alpha, t.T[k]) - beta;
+        float diff = fmaf(-v[s][k], alpha, T[k]) - beta;
         diff = diff * diff;
-        p = fmaf(diff, t.mkT[k], p);
+        p = fmaf(diff, mkT[k], p);
       }
       part[s] = p;
     }
@@ -326,9 +336,9 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
         const float vv = S.v[(s * SFE_SLOTS + k) * 32 + lane];
-        float diff = fmaf(-vv, alpha, t.T[k]) - beta;
+        float diff = fmaf(-vv, alpha, T[k]) - beta;
         diff = diff * diff;
-        const float q = fmaf(diff, t.mkT[k], p);
+        const float q = fmaf(diff, mkT[k], p);
         p = vv == 0.f ? p : q;
       }
 #pragma unroll
@@ -452,7 +462,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) get_patches_kernel(PyrView v, 
   evaluate(scratch[warp], img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, d);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
-    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = t.T[k];
+    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = scratch[warp].T[k * 32 + lane];
   if (lane == 0) { mean[i] = t.mean; sumsq[i] = t.sumsq; }
 }
 
