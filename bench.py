@@ -34,6 +34,17 @@ WORKLOAD = "C2: 640x480 frame pairs, 2000 features/pair, 4-level pyramid (both f
            "Hessian patch tracking + 2000x2000 256-bit Hamming top-2"
 
 
+def measured_traffic(kernel, batch):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic_r1.json), only when the
+    capture was taken at this batch size; None otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            e = json.load(f)[kernel]
+        return float(e["dram_bytes"]) if int(e["batch_pairs"]) == int(batch) else None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -280,7 +291,8 @@ def run_gpu(args):
             # dominant kernel: track_fb_kernel (one launch per step). Latency/issue bound, NOT HBM bound
             # (pyramids are read once and then live in L1/L2) -- the fraction is reported as asked.
             "roofline": {"kernel": "track_fb_kernel<HESSIAN>", "bound": "hbm", "achieved": trk_bytes / (trk_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": trk_bytes / (trk_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": trk_bytes / (trk_ms * 1e-3) / 1e9 / peak,
+                         "traffic": measured_traffic("track_fb_kernel", B), "algorithmic_bytes": trk_bytes,
                          "peak_source": peak_src, "share_of_step": trk_ms / ms_step,
                          "bilinear_samples_per_sec": newton * 6 * 169 / args.steps / 1.0 / (trk_ms * 1e-3) if False else
                          (newton * 6 * 169) / (trk_ms * 1e-3)},

@@ -152,6 +152,26 @@ __device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& 
   }
 }
 
+// Correctly rounded division by a CONSTANT without the division sequence: with y = RN(1/d),
+// q = RN(x*y), r = x - q*d (exact in one FMA) and q' = RN(q + r*y), q' equals RN(x/d) (Markstein's
+// theorem for a correctly rounded reciprocal; no overflow/underflow at the magnitudes of patch sums and
+// scores).  Verified rather than trusted: x/169.f exhaustively over all 2^32 floats (the only difference
+// is x = -0, which a sum of non-negative terms never is), x/0.02 over 6.4e9 doubles of the forms that
+// occur here (float differences, halves, quotient differences) -- tools/check_const_div.c.  The oracle keeps
+// the reference's plain divisions (hessian.h:88-89, :163-169); parity tests compare bit patterns.
+__device__ __forceinline__ float div169(float x) {
+  const float d = (float)SFE_PLEN, y = 1.0f / (float)SFE_PLEN;
+  const float q = x * y;
+  const float r = fmaf(-q, d, x);
+  return fmaf(r, y, q);
+}
+__device__ __forceinline__ double div_h(double x) {
+  const double h = 0.02, y = 1.0 / 0.02;
+  const double q = __dmul_rn(x, y);
+  const double r = __fma_rn(-q, h, x);
+  return __fma_rn(r, y, q);
+}
+
 // Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
 // returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
 __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
@@ -170,16 +190,15 @@ __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
 __device__ __forceinline__ void finite_differences(float sc, int lane, float (&d)[6]) {
   constexpr unsigned PA = 0x55040343u, MA = 0x34201021u;  // minuend / subtrahend score of quotient j (nibbles)
   constexpr unsigned PB = 0x7642u, MB = 0x4253u;          // dxx,dyy,dxy,dyx: minuend / subtrahend quotient
-  const double h = 0.02;
   const int j = lane & 7;
   const double p = (double)__shfl_sync(SFE_FULL, sc, 4 * ((PA >> (4 * j)) & 7));
   const double m = (double)__shfl_sync(SFE_FULL, sc, 4 * ((MA >> (4 * j)) & 7));
   double num = __dsub_rn(p, m);
   if (j < 2) num = __dmul_rn(0.5, num);
-  const double q = __ddiv_rn(num, h);
+  const double q = div_h(num);
   const int jb = lane & 3;
   const double qp = __shfl_sync(SFE_FULL, q, (PB >> (4 * jb)) & 7), qm = __shfl_sync(SFE_FULL, q, (MB >> (4 * jb)) & 7);
-  const double r = __ddiv_rn(__dsub_rn(qp, qm), h);
+  const double r = div_h(__dsub_rn(qp, qm));
   const float qf = (float)q, rf = (float)r;
   d[0] = __shfl_sync(SFE_FULL, qf, 0);
   d[1] = __shfl_sync(SFE_FULL, qf, 1);
@@ -240,7 +259,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
       S.T[k * 32 + lane] = v;
       S.mkT[k * 32 + lane] = v == 0.f ? 0.f : m;
     }
-    const float red = packed_reduce2(sm, sq, lane) / (float)SFE_PLEN;
+    const float red = div169(packed_reduce2(sm, sq, lane));
     t.mean = __shfl_sync(SFE_FULL, red, 0);
     t.sumsq = __shfl_sync(SFE_FULL, red, 16);
     return 0.f;
@@ -301,7 +320,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool
   // lane-parallel alpha/beta (hessian.h:131-132): lanes 2s (s < 6) hold the values of shift s; lanes >= 12
   // hold padding and get benign operands so the IEEE divide/sqrt stay on their fast paths
   const bool live = lane < 12;
-  const float mean = red / (float)SFE_PLEN, sumsq = live ? other / (float)SFE_PLEN : 1.f;
+  const float mean = div169(red), sumsq = live ? div169(other) : 1.f;
   const float alpha_l = sqrtf((live ? t.sumsq : 1.f) / sumsq);
   const float beta_l = t.mean - alpha_l * mean;
   float part[8];
