@@ -216,17 +216,31 @@ struct Tmpl {
   float mean, sumsq;
 };
 
+// Which footprint the shared tile currently holds (warp-uniform).
+struct TileTag {
+  const float* img;
+  unsigned key;
+};
+
 // One patch evaluation at (x,y) of image `im`:
 //   is_tmpl   GetPatch (hessian.h:54-93): t <- the patch, its statistics and its effective mask
 //   otherwise BruteHessian (hessian.h:147-172) against the template t: the six derivatives
 //             d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as the reference stores them through
 //             float*); returns sad0.
-__device__ __forceinline__ float evaluate(WarpScratch& S, const ImgView im, bool is_tmpl, Tmpl& t,
+__device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const ImgView im, bool is_tmpl, Tmpl& t,
                                           const float* __restrict__ mask, float x, float y, int lane, float (&d)[6]) {
   __syncwarp();
   const AxisGeom g = lane_geom(x, y, lane);
   const int ox = (int)floorf(x) - 7, oy = (int)floorf(y) - 7;
-  const bool nonpos = stage_tile(S, im, ox, oy, lane);
+  // a Newton step moves the point by at most one pixel, so consecutive steps usually share their footprint:
+  // restage only when the image or the footprint origin changed
+  const unsigned key = (unsigned)(ox + 0x4000) | ((unsigned)(oy + 0x4000) << 15);  // 15 bits each, bit 31 = nonpos
+  if (tag.img != im.p || (tag.key & 0x7fffffffu) != key) {
+    const bool np = stage_tile(S, im, ox, oy, lane);
+    tag.img = im.p;
+    tag.key = key | (np ? 0x80000000u : 0u);
+  }
+  const bool nonpos = tag.key >> 31;
   const int ix = __shfl_sync(SFE_FULL, g.i0, 0), iy = __shfl_sync(SFE_FULL, g.i0, 4);
   const bool mine = (lane & 3) != 3 && lane < 8;
   const int ibase = __shfl_sync(SFE_FULL, g.i0, lane & 4), rbase = __shfl_sync(SFE_FULL, g.r, lane & 4);
@@ -376,7 +390,7 @@ __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
 
 // GetPatches (hessian.h:175-183) on the template pyramid + TrackFeature (hessian.h:243-264) with Track
 // (hessian.h:185-241) on the search pyramid.  (x,y) is updated only on success.
-__device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, int tframe, float tx, float ty,
+__device__ __forceinline__ int track_feature(WarpScratch& S, TileTag& tag, const PyrView& tp, int tframe, float tx, float ty,
                                              const PyrView& sp, int sframe, int levels, float thr, int maxit,
                                              const float* __restrict__ mask, float& x, float& y, int lane, int& steps) {
   const int lv = min(min(tp.depth, sp.depth), levels);
@@ -398,7 +412,7 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, const PyrView& tp, 
       im.p = is_tmpl ? tim.p : sim.p;
       im.w = sim.w; im.h = sim.h; im.pitch = sim.pitch;  // both pyramids have the same geometry
       float d[6];
-      evaluate(S, im, is_tmpl, t, mask, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, d);
+      evaluate(S, tag, im, is_tmpl, t, mask, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, d);
       if (is_tmpl) continue;
       ++steps;
       float dx, dy;
@@ -437,6 +451,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
     const int lv = a.levels ? a.levels[i] : a.default_levels;
     int steps = 0;
     int st[2];
+    TileTag tag{nullptr, 0u};
     float bx = fx, by = fy;  // matcher.cpp:181
     // dir 0: template from `from` at from_pt, search `to` from the seed (matcher.cpp:175-176)
     // dir 1: template from `to` at the forward result, search `from` from from_pt (matcher.cpp:180-182)
@@ -446,7 +461,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
       const PyrView& tp = dir == 0 ? from : to;
       const PyrView& sp = dir == 0 ? to : from;
       float x = dir == 0 ? tx : bx, y = dir == 0 ? ty : by;
-      const int s = track_feature(S, tp, dir == 0 ? ff : tf, dir == 0 ? fx : tx, dir == 0 ? fy : ty, sp,
+      const int s = track_feature(S, tag, tp, dir == 0 ? ff : tf, dir == 0 ? fx : tx, dir == 0 ? fy : ty, sp,
                                   dir == 0 ? tf : ff, lv, a.thr, a.maxit, mask, x, y, lane, steps);
       if (dir == 0) { tx = x; ty = y; st[0] = s; } else { bx = x; by = y; st[1] = s; }
     }
@@ -478,7 +493,8 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) get_patches_kernel(PyrView v, 
   init_scratch(scratch[warp], lane);
   float d[6];
   Tmpl t;
-  evaluate(scratch[warp], img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, d);
+  TileTag tag{nullptr, 0u};
+  evaluate(scratch[warp], tag, img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, d);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
     if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = scratch[warp].T[k * 32 + lane];
@@ -497,8 +513,9 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
   init_scratch(scratch[warp], lane);
   Tmpl t;
   float d[6];
-  evaluate(scratch[warp], img_of(tv, 0, level, tframe), true, t, mask, txy[2 * i], txy[2 * i + 1], lane, d);
-  const float s0 = evaluate(scratch[warp], img_of(sv, 0, level, sframe), false, t, mask, xy[2 * i], xy[2 * i + 1], lane, d);
+  TileTag tag{nullptr, 0u};
+  evaluate(scratch[warp], tag, img_of(tv, 0, level, tframe), true, t, mask, txy[2 * i], txy[2 * i + 1], lane, d);
+  const float s0 = evaluate(scratch[warp], tag, img_of(sv, 0, level, sframe), false, t, mask, xy[2 * i], xy[2 * i + 1], lane, d);
   if (lane == 0) {
     out7[7 * i] = s0;
     for (int k = 0; k < 6; ++k) out7[7 * i + 1 + k] = d[k];
