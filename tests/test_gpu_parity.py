@@ -263,3 +263,57 @@ def test_hamming_bit_exact(fe, po, synth, nq, nt, batch):
         oi, od, oo = po.hamming256_top2(q[b * nq:(b + 1) * nq], t[b * nt:(b + 1) * nt], 4, 5, 80)
         sl = slice(b * nq, (b + 1) * nq)
         assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od) and np.array_equal(ok[sl], oo)
+
+
+def test_config3_1080p_8_levels_5000_features_bit_exact(fe, po, synth):
+    """BASELINE config 3: 1920x1080 pair, 5000 features, 8-level pyramid (1920 ... 15x9) -- pyramids of both
+    frames and the forward/backward tracks against the oracle, bit for bit."""
+    H, W, n = 1080, 1920, 5000
+    A, B = synth.make_pairs(5, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    pts = _features(synth, n, H, W, seed=21, border=0.05)
+    ga, gb = fe.make_pyramid(A, 8), fe.make_pyramid(B, 8)
+    oa, ob = po.Pyramid(A, 8), po.Pyramid(B, 8)
+    for l in range(8):
+        assert_bits_equal(gb.plane(l), ob.plane(l), "frame B level %d" % l)
+    g = fe.track_fb(ga, gb, pts, pts, 8)
+    o = po.hes_track_fb(oa, ob, pts, pts, 8)
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(g[k], o[k]), k
+    assert_bits_equal(g["to_xy"], o["to_xy"], "to_xy")
+    assert_bits_equal(g["back_xy"], o["back_xy"], "back_xy")
+    assert int(g["steps"].sum()) == o["newton_steps"]
+    assert g["accepted"].mean() > 0.8
+
+
+def test_config5_hamming_1m_x_1m_properties(fe, po, synth):
+    """BASELINE config 5 at full size on one GPU (10^12 comparisons): the oracle cannot finish that, so the result is
+    checked through size-independent properties -- planted duplicates are found at distance 0 at the LOWEST train index
+    that holds them, distances are ordered, the ratio flag is consistent with the returned distances -- and 256 randomly
+    chosen query rows are compared with the oracle outright."""
+    n = 1 << 20
+    t = synth.make_descriptors(11, n, dup_frac=0.001)
+    q = synth.make_descriptors(12, n, dup_frac=0.0)
+    rng = np.random.default_rng(7)
+    planted = rng.choice(n, 4096, replace=False)
+    src = rng.integers(0, n, 4096)
+    q[planted] = t[src]
+    idx, dist, ok = fe.match_hamming256(q, t, 4, 5, 80)
+    assert idx.shape == (n, 2) and (idx >= 0).all() and (idx < n).all()
+    assert (dist[:, 0] <= dist[:, 1]).all() and (dist >= 0).all() and (dist <= 256).all()
+    assert (idx[:, 0] != idx[:, 1]).all()
+    # planted rows: distance 0, and the winner holds the same descriptor at an index <= the planted source
+    assert (dist[planted, 0] == 0).all()
+    assert (idx[planted, 0] <= src).all()
+    assert (t[idx[planted, 0]] == t[src]).all()
+    # distances recomputed on the host for every query row agree with the returned indices
+    pop = np.array([bin(i).count("1") for i in range(256)], np.uint8)
+    for col in (0, 1):
+        x = (q ^ t[idx[:, col]]).view(np.uint8)
+        assert np.array_equal(pop[x].reshape(n, 32).sum(1).astype(np.int32), dist[:, col]), "column %d" % col
+    exp_ok = (dist[:, 0] <= 80) & (dist[:, 0].astype(np.int64) * 5 < dist[:, 1].astype(np.int64) * 4)
+    assert np.array_equal(ok.astype(bool), exp_ok)
+    # spot check against the oracle
+    rows = np.concatenate([planted[:64], rng.choice(n, 192, replace=False)])
+    oi, od, oo = po.hamming256_top2(q[rows], t, 4, 5, 80)
+    assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od) and np.array_equal(ok[rows], oo)
