@@ -210,6 +210,20 @@ int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const ui
                      float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
                      int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
 
+/* ---- corner seeding (the step after tracking on keyframes) -------------------------------- */
+
+/* Replaces cv::cvtColor(img, grey, CV_RGB2GRAY) + cv::goodFeaturesToTrack(grey, corners, max_corners,
+ * quality, min_distance) of matcher.cpp:313 and :123-130 (defaults: min-eigenvalue response, blockSize 3,
+ * 3x3 Sobel, no mask) for `count` BGR frames.  corners [count][max_corners][2] (x,y as cv::Point2f,
+ * strongest first), ncorners [count].  The reference calls it with 120, 0.01, 20.
+ * eig_out (host variant only, may be NULL): the cornerMinEigenVal response maps [count][h][w]. */
+int sfe_good_features(sfe_ctx* ctx, const uint8_t* bgr_host, int w, int h, size_t row_stride,
+                      size_t frame_stride, int count, int max_corners, double quality,
+                      double min_distance, float* corners, int32_t* ncorners, float* eig_out);
+int sfe_good_features_dev(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stride,
+                          size_t frame_stride, int count, int max_corners, double quality,
+                          double min_distance, float* corners, int32_t* ncorners);
+
 #ifdef __cplusplus
 }
 #endif

@@ -523,6 +523,153 @@ int orc_hes_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float*
   return nacc;
 }
 
+/* ------------------------------------------------------------------ corner seeding */
+
+/* cv::cornerMinEigenVal(gray8, blockSize 3, ksize 3) as cv::goodFeaturesToTrack calls it (matcher.cpp:125 ->
+ * featureselect.cpp -> corner.cpp cornerEigenValsVecs), BORDER_REFLECT_101 everywhere:
+ *   Dx = Sobel(1,0) * s, Dy = Sobel(0,1) * s with s = 1/(4*3*255); OpenCV scales the COLUMN kernel of Dx
+ *        and the ROW kernel of Dy:  Dx = fma(r(-1)+r(+1), s, r(0)*2s), r = g(x+1)-g(x-1)
+ *                                   Dy = q(+1)-q(-1),  q = fma(g(x+1), s, fma(g(x), 2s, g(x-1)*s))
+ *   cov = (Dx*Dx, Dx*Dy, Dy*Dy) in float;  3x3 box sums accumulate in DOUBLE: row sums (c(-1)+c(0))+c(+1),
+ *        then OpenCV's running column sum from the top of the image: S = (0+R(-1))+R(0); D(y) = S+R(y+1);
+ *        S = D(y)-R(y-1)  -- history dependent in the last bit of the double, reproduced here;
+ *   eig = (a+c) - sqrt((a-c)*(a-c) + b*b), a = 0.5*Sxx, b = Sxy, c = 0.5*Syy, float, no FMA.
+ * Probed bit-for-bit against cv2 4.13 for widths that are a multiple of 16 (the right-most W mod 16 columns
+ * of cv2 run scalar code whose Dy row filter is not fused; the SIMD formula is used uniformly here). */
+void orc_min_eigen_val(const uint8_t* gray, int w, int h, float* eig) {
+  const double sd = 1.0 / (4.0 * 3.0 * 255.0);
+  const float k0 = (float)sd, k1 = (float)(2.0 * sd);
+  float* r = (float*)malloc(sizeof(float) * (size_t)w * (h + 2));  /* horizontal difference rows -1..h */
+  float* q = (float*)malloc(sizeof(float) * (size_t)w * (h + 2));  /* horizontally smoothed rows -1..h */
+  for (int yy = -1; yy <= h; ++yy) {
+    const uint8_t* g = gray + (size_t)reflect101(yy, h) * w;
+    float* rr = r + (size_t)(yy + 1) * w;
+    float* qq = q + (size_t)(yy + 1) * w;
+    for (int x = 0; x < w; ++x) {
+      const float a = (float)g[reflect101(x - 1, w)], b = (float)g[x], c = (float)g[reflect101(x + 1, w)];
+      rr[x] = c - a;
+      qq[x] = fmaf(c, k0, fmaf(b, k1, a * k0));
+    }
+  }
+  float* cov = (float*)malloc(sizeof(float) * 3 * (size_t)w * h);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const float* r0 = r + (size_t)y * w;  /* row y-1 */
+      const float* q0 = q + (size_t)y * w;
+      const float dx = fmaf(r0[x] + r0[2 * (size_t)w + x], k0, r0[w + x] * k1);
+      const float dy = q0[2 * (size_t)w + x] - q0[x];
+      float* c = cov + 3 * ((size_t)y * w + x);
+      c[0] = dx * dx; c[1] = dx * dy; c[2] = dy * dy;
+    }
+  free(r); free(q);
+  /* box filter: double row sums R(y)[x][ch] for rows -1..h, then the running column sum */
+  double* R = (double*)malloc(sizeof(double) * 3 * (size_t)w * (h + 2));
+  for (int yy = -1; yy <= h; ++yy) {
+    const float* c = cov + 3 * (size_t)reflect101(yy, h) * w;
+    double* o = R + 3 * (size_t)(yy + 1) * w;
+    for (int x = 0; x < w; ++x)
+      for (int ch = 0; ch < 3; ++ch)
+        o[3 * x + ch] = ((double)c[3 * reflect101(x - 1, w) + ch] + (double)c[3 * x + ch]) + (double)c[3 * reflect101(x + 1, w) + ch];
+  }
+  double* S = (double*)calloc(3 * (size_t)w, sizeof(double));
+  for (size_t i = 0; i < 3 * (size_t)w; ++i) S[i] = (0.0 + R[i]) + R[3 * (size_t)w + i];
+  for (int y = 0; y < h; ++y) {
+    const double* Rp = R + 3 * (size_t)(y + 2) * w;  /* row y+1 */
+    const double* Rm = R + 3 * (size_t)y * w;        /* row y-1 */
+    for (int x = 0; x < w; ++x) {
+      float box[3];
+      for (int ch = 0; ch < 3; ++ch) {
+        const double s = S[3 * x + ch] + Rp[3 * x + ch];
+        box[ch] = (float)s;
+        S[3 * x + ch] = s - Rm[3 * x + ch];
+      }
+      const float a = box[0] * 0.5f, b = box[1], c = box[2] * 0.5f;
+      const float t = a - c;
+      eig[(size_t)y * w + x] = (a + c) - sqrtf(t * t + b * b);
+    }
+  }
+  free(S); free(R); free(cov);
+}
+
+typedef struct { float v; int ofs; } orc_cand;
+static int cand_cmp(const void* pa, const void* pb) {
+  /* featureselect.cpp greaterThanPtr: larger value first, ties by HIGHER address first */
+  const orc_cand* a = (const orc_cand*)pa; const orc_cand* b = (const orc_cand*)pb;
+  if (a->v > b->v) return -1;
+  if (a->v < b->v) return 1;
+  return a->ofs > b->ofs ? -1 : (a->ofs < b->ofs ? 1 : 0);
+}
+
+/* cv::goodFeaturesToTrack(gray, corners, max_corners, quality, min_distance) with its defaults (blockSize 3,
+ * min-eigenvalue response, no mask) -- matcher.cpp:123-130 on the RGB2GRAY image of matcher.cpp:313.
+ * corners_xy holds max_corners (x,y) pairs (max_corners must be > 0); returns the number found.  eig_out
+ * (w*h, may be NULL) receives the response map, max_out its maximum. */
+int orc_good_features(const uint8_t* bgr, int w, int h, size_t stride, int max_corners, double quality,
+                      double min_distance, float* corners_xy, float* eig_out, float* max_out) {
+  uint8_t* gray = (uint8_t*)malloc((size_t)w * h);
+  orc_gray_u8(bgr, w, h, stride, gray);
+  float* eig = eig_out ? eig_out : (float*)malloc(sizeof(float) * (size_t)w * h);
+  orc_min_eigen_val(gray, w, h, eig);
+  free(gray);
+  float mx = eig[0];                                   /* minMaxLoc */
+  for (size_t i = 1; i < (size_t)w * h; ++i) if (eig[i] > mx) mx = eig[i];
+  if (max_out) *max_out = mx;
+  const float thr = (float)((double)mx * quality);     /* threshold(..., THRESH_TOZERO) compares in float */
+  /* local maxima of the thresholded map under a 3x3 dilation, interior pixels only (featureselect.cpp) */
+  orc_cand* cand = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)w * h);
+  size_t nc = 0;
+#define TZ(v) ((v) > thr ? (v) : 0.f)
+  for (int y = 1; y < h - 1; ++y)
+    for (int x = 1; x < w - 1; ++x) {
+      const float v = TZ(eig[(size_t)y * w + x]);
+      if (v == 0.f) continue;
+      float m = v;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const float n = TZ(eig[(size_t)(y + dy) * w + x + dx]);
+          if (n > m) m = n;
+        }
+      if (v == m) { cand[nc].v = v; cand[nc].ofs = y * w + x; ++nc; }
+    }
+#undef TZ
+  qsort(cand, nc, sizeof(orc_cand), cand_cmp);
+  int n = 0;
+  if (min_distance >= 1) {
+    const int cell = (int)lrint(min_distance);         /* cvRound */
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    int* head = (int*)malloc(sizeof(int) * (size_t)gw * gh);  /* per cell: linked list through next[] */
+    int* next = (int*)malloc(sizeof(int) * (size_t)max_corners);
+    for (int i = 0; i < gw * gh; ++i) head[i] = -1;
+    const double md2 = min_distance * min_distance;
+    for (size_t i = 0; i < nc && n < max_corners; ++i) {
+      const int y = cand[i].ofs / w, x = cand[i].ofs - y * w;
+      const int xc = x / cell, yc = y / cell;
+      const int x1 = xc > 0 ? xc - 1 : 0, y1 = yc > 0 ? yc - 1 : 0;
+      const int x2 = xc + 1 < gw ? xc + 1 : gw - 1, y2 = yc + 1 < gh ? yc + 1 : gh - 1;
+      int good = 1;
+      for (int yy = y1; yy <= y2 && good; ++yy)
+        for (int xx = x1; xx <= x2 && good; ++xx)
+          for (int j = head[yy * gw + xx]; j >= 0; j = next[j]) {
+            const float dx = (float)x - corners_xy[2 * j], dy = (float)y - corners_xy[2 * j + 1];
+            if ((double)(dx * dx + dy * dy) < md2) { good = 0; break; }
+          }
+      if (!good) continue;
+      corners_xy[2 * n] = (float)x; corners_xy[2 * n + 1] = (float)y;
+      next[n] = head[yc * gw + xc]; head[yc * gw + xc] = n;
+      ++n;
+    }
+    free(head); free(next);
+  } else {
+    for (size_t i = 0; i < nc && n < max_corners; ++i, ++n) {
+      const int y = cand[i].ofs / w, x = cand[i].ofs - y * w;
+      corners_xy[2 * n] = (float)x; corners_xy[2 * n + 1] = (float)y;
+    }
+  }
+  free(cand);
+  if (!eig_out) free(eig);
+  return n;
+}
+
 /* ------------------------------------------------------------------ P2 KLTTracker */
 
 /* klt.h:59-96: three full 13x13 getRectSubPix calls, no edge clipping. */

@@ -134,6 +134,12 @@ int orc_brute_track(const orc_pyr* from, const orc_pyr* to, int n, const float* 
                     int n_fine, int* status, float* best_sad, int64_t* npos, int nthreads);
 
 /* ---- P4: Hamming ----------------------------------------------------------- */
+/* Corner seeding: cv::cornerMinEigenVal(gray8, 3, 3) and cv::goodFeaturesToTrack with
+ * its defaults, as matcher.cpp:123-130 calls them; probed bit-for-bit against cv2 4.13 (see oracle.c). */
+void orc_min_eigen_val(const uint8_t* gray, int w, int h, float* eig);
+int orc_good_features(const uint8_t* bgr, int w, int h, size_t stride, int max_corners, double quality,
+                      double min_distance, float* corners_xy, float* eig_out, float* max_out);
+
 /* q: nq x 8 u32, t: nt x 8 u32.  idx/dist: nq x 2 (best, second); lowest train index wins
  * ties; missing neighbours are idx -1 / dist 257.  pass[i] = d1 <= max_dist &&
  * d1*ratio_den < d2*ratio_num (integer ratio test). */

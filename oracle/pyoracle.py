@@ -92,6 +92,8 @@ def lib(fast=False, native=False):
     L.orc_brute_track.argtypes = [vp, vp, C.c_int, f32p, f32p, f32p, C.c_int, f32p, C.c_int, i32p, f32p, i64p,
                                   C.c_int]
     L.orc_brute_track.restype = C.c_int
+    L.orc_min_eigen_val.argtypes = [u8p, C.c_int, C.c_int, f32p]
+    L.orc_good_features.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, f32p, f32p, f32p]
     L.orc_hamming256_top2.argtypes = [u32p, C.c_int, u32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, u8p,
                                       C.c_int]
     L.orc_num_threads.restype = C.c_int
@@ -299,3 +301,24 @@ def hamming256_top2(q, t, ratio_num=4, ratio_den=5, max_dist=256, nthreads=0, fa
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def min_eigen_val(gray):
+    """cv::cornerMinEigenVal(gray8, blockSize 3, ksize 3)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.empty((h, w), np.float32)
+    lib().orc_min_eigen_val(_p(gray, C.c_uint8), w, h, _p(out, C.c_float))
+    return out
+
+
+def good_features(bgr, max_corners=120, quality=0.01, min_distance=20.0, want_eig=False):
+    """cv::goodFeaturesToTrack on the RGB2GRAY image of a BGR frame (matcher.cpp:313 + :123-130)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    xy = np.zeros((max_corners, 2), np.float32)
+    eig = np.empty((h, w), np.float32)
+    mx = np.zeros(1, np.float32)
+    n = lib().orc_good_features(_p(bgr, C.c_uint8), w, h, bgr.strides[0], max_corners, float(quality), float(min_distance),
+                                _p(xy, C.c_float), _p(eig, C.c_float), _p(mx, C.c_float))
+    return (xy[:n].copy(), eig, float(mx[0])) if want_eig else xy[:n].copy()

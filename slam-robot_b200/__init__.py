@@ -32,7 +32,7 @@ EXPORTS = [
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
-    "sfe_match_hamming256_async", "sfe_replay_pairs",
+    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_good_features", "sfe_good_features_dev",
 ]
 
 
@@ -111,6 +111,8 @@ def lib():
     L.sfe_match_hamming256.argtypes = ham
     L.sfe_match_hamming256_dev.argtypes = ham
     L.sfe_match_hamming256_async.argtypes = ham
+    L.sfe_good_features.argtypes = [vp, vp, i32, i32, sz, sz, i32, i32, C.c_double, C.c_double, vp, vp, vp]
+    L.sfe_good_features_dev.argtypes = [vp, vp, i32, i32, sz, sz, i32, i32, C.c_double, C.c_double, vp, vp]
     L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
                                    vp, vp, i32]
     _lib = L
@@ -336,6 +338,29 @@ class FrontEnd:
                                           maxit, fb_max, _ptr(out["back_xy"]), _ptr(out["status_fwd"]), _ptr(out["status_bwd"]),
                                           _ptr(out["accepted"]), _ptr(out.get("steps")), int(chunk_pairs)))
         return out
+
+    # ---- corner seeding (matcher.cpp:313 + :123-130: RGB2GRAY + goodFeaturesToTrack)
+    def good_features(self, frames, max_corners=120, quality=0.01, min_distance=20.0, want_eig=False):
+        """frames: (n,H,W,3) or (H,W,3) uint8; numpy -> host path (returns per-frame corner arrays, optionally the
+        response maps), CUDA tensor -> device path (returns (corners[n,max,2], ncorners[n]) tensors)."""
+        if frames.ndim == 3:
+            frames = frames[None]
+        n, H, W, _ = frames.shape
+        if _is_torch(frames) and frames.is_cuda:
+            import torch
+            xy = torch.zeros((n, max_corners, 2), dtype=torch.float32, device=frames.device)
+            cnt = torch.zeros(n, dtype=torch.int32, device=frames.device)
+            self._chk(self.L.sfe_good_features_dev(self.h, frames.data_ptr(), W, H, 3 * W, 3 * W * H, n, max_corners,
+                                                   float(quality), float(min_distance), xy.data_ptr(), cnt.data_ptr()))
+            return xy, cnt
+        frames = np.ascontiguousarray(frames, np.uint8)
+        xy = np.zeros((n, max_corners, 2), np.float32)
+        cnt = np.zeros(n, np.int32)
+        eig = np.empty((n, H, W), np.float32) if want_eig else None
+        self._chk(self.L.sfe_good_features(self.h, _ptr(frames), W, H, 3 * W, 3 * W * H, n, max_corners, float(quality),
+                                           float(min_distance), _ptr(xy), _ptr(cnt), _ptr(eig)))
+        corners = [xy[i, :cnt[i]].copy() for i in range(n)]
+        return (corners, eig) if want_eig else corners
 
     def pinned(self, shape, dtype):
         """A page-locked host array (sfe_host_alloc): lets the host-pointer entry points copy asynchronously."""

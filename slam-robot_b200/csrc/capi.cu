@@ -181,6 +181,7 @@ void sfe_destroy(sfe_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
   if (ctx->ham_io) cudaFree(ctx->ham_io);
+  if (ctx->gftt_ws) cudaFree(ctx->gftt_ws);
   cudaFree(ctx->d_mask);
   cudaFree(ctx->d_counter);
   cudaStreamDestroy(ctx->own_stream);
@@ -616,6 +617,91 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
   CU(cudaMemcpyAsync(idx, d_i, ob, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(dist, d_d, ob, cudaMemcpyDeviceToHost, s));
   if (pass) CU(cudaMemcpyAsync(pass, d_p, (size_t)nq * batch, cudaMemcpyDeviceToHost, s));
+  return SFE_SUCCESS;
+}
+
+/* ---- corner seeding -------------------------------------------------- */
+
+namespace {
+int gftt_cap(int w, int h) {  // candidate capacity per frame: a power of two >= w*h/8 (the bitonic sort pads to one)
+  int cap = 1024;
+  while (cap < (w / 8 + 1) * h) cap <<= 1;
+  return cap;
+}
+size_t gftt_ws_bytes(int w, int h, int count) {
+  return padded(sizeof(float) * (size_t)w * h * count) + 2 * padded(sizeof(int) * (size_t)count) +
+         padded(sizeof(unsigned long long) * (size_t)gftt_cap(w, h) * count);
+}
+int gftt_run(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stride, size_t frame_stride, int count,
+             int max_corners, double quality, double min_distance, float* corners_dev, int32_t* ncorners_dev, float** eig_dev) {
+  const size_t need = gftt_ws_bytes(w, h, count);
+  if (need > ctx->gftt_cap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gftt_ws) CU(cudaFree(ctx->gftt_ws));
+    ctx->gftt_ws = nullptr;
+    ctx->gftt_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->gftt_ws, need);
+    if (e != cudaSuccess) return fail(ctx, SFE_ERR_NOMEM, "cudaMalloc(corner workspace): %s", cudaGetErrorString(e));
+    ctx->gftt_cap = need;
+  }
+  Carver c{(char*)ctx->gftt_ws, 0};
+  float* eig = c.take<float>((size_t)w * h * count);
+  unsigned* mx = c.take<unsigned>(count);
+  int* nc = c.take<int>(count);
+  unsigned long long* keys = c.take<unsigned long long>((size_t)gftt_cap(w, h) * count);
+  if (eig_dev) *eig_dev = eig;
+  return launched(ctx,
+                  launch_good_features(bgr_dev, row_stride, frame_stride, w, h, count, max_corners, quality, min_distance, eig, mx,
+                                       nc, keys, gftt_cap(w, h), corners_dev, ncorners_dev, ctx->stream),
+                  "good_features launch: %s");
+}
+bool gftt_args_ok(int w, int h, size_t row_stride, int count, int max_corners, double quality, double min_distance) {
+  return w >= 16 && h >= 16 && row_stride >= (size_t)3 * w && count >= 0 && max_corners >= 1 && max_corners <= 24000 &&
+         quality > 0 && min_distance >= 0;
+}
+}  // namespace
+
+int sfe_good_features_dev(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stride, size_t frame_stride, int count,
+                          int max_corners, double quality, double min_distance, float* corners, int32_t* ncorners) {
+  if (!ctx || !bgr_dev || !corners || !ncorners || !gftt_args_ok(w, h, row_stride, count, max_corners, quality, min_distance))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad good_features arguments");
+  if (count == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return gftt_run(ctx, bgr_dev, w, h, row_stride, frame_stride, count, max_corners, quality, min_distance, corners, ncorners, nullptr);
+}
+
+int sfe_good_features(sfe_ctx* ctx, const uint8_t* bgr_host, int w, int h, size_t row_stride, size_t frame_stride, int count,
+                      int max_corners, double quality, double min_distance, float* corners, int32_t* ncorners, float* eig_out) {
+  if (!ctx || !bgr_host || !corners || !ncorners || !gftt_args_ok(w, h, row_stride, count, max_corners, quality, min_distance))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad good_features arguments");
+  if (count == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  const size_t dense_row = (size_t)3 * w, dense_frame = dense_row * h;
+  const size_t need = padded(dense_frame * count) + padded(8 * (size_t)max_corners * count) + padded(4 * (size_t)count);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  uint8_t* d_bgr = c.take<uint8_t>(dense_frame * count);
+  float* d_xy = c.take<float>(2 * (size_t)max_corners * count);
+  int32_t* d_n = c.take<int32_t>(count);
+  cudaStream_t s = ctx->stream;
+  if (row_stride == dense_row && (frame_stride == dense_frame || count == 1)) {
+    CU(cudaMemcpyAsync(d_bgr, bgr_host, dense_frame * count, cudaMemcpyHostToDevice, s));
+  } else {
+    for (int f = 0; f < count; ++f)
+      CU(cudaMemcpy2DAsync(d_bgr + f * dense_frame, dense_row, bgr_host + f * frame_stride, row_stride, dense_row, h,
+                           cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemsetAsync(d_xy, 0, 8 * (size_t)max_corners * count, s));
+  float* d_eig = nullptr;
+  rc = gftt_run(ctx, d_bgr, w, h, dense_row, dense_frame, count, max_corners, quality, min_distance, d_xy, d_n, &d_eig);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(corners, d_xy, 8 * (size_t)max_corners * count, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(ncorners, d_n, 4 * (size_t)count, cudaMemcpyDeviceToHost, s));
+  if (eig_out) CU(cudaMemcpyAsync(eig_out, d_eig, sizeof(float) * (size_t)w * h * count, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int f = 0; f < count; ++f)
+    if (ncorners[f] < 0) return fail(ctx, SFE_ERR_INVALID, "%s", "corner candidate list overflowed (raise quality)");
   return SFE_SUCCESS;
 }
 

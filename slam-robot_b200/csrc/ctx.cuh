@@ -21,6 +21,8 @@ struct sfe_ctx {
   size_t ham_io_cap;
   int64_t launches;
   sfe_replay* replay;  // lazily created by sfe_replay_pairs
+  void* gftt_ws;   // corner-seeding workspace: response maps, maxima, candidate keys
+  size_t gftt_cap;
   char err[512];
 };
 

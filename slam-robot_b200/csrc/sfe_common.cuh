@@ -105,3 +105,6 @@ int launch_brute_track(const PyrView& from, const PyrView& to, int from_first, i
 int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int ratio_num,
                       int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass,
                       void** ws, size_t* ws_cap, cudaStream_t s);
+int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_stride, int w, int h, int count, int max_corners,
+                         double quality, double min_distance, float* eig, unsigned* max_code, int* ncand,
+                         unsigned long long* keys, int cap, float* corners, int* ncorners, cudaStream_t s);

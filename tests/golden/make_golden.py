@@ -12,6 +12,8 @@ against outputs of the OpenCV primitives the reference calls (hessian.h / klt.h 
   tracks.npz      forward/backward tracks (matcher.cpp:173-206) from tier-0 ON THE cv2 PLANES
                   (the oracle must reproduce them bit-exactly when given the same planes)
   hamming.npz     cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) on seeded descriptors with planted ties
+  corners.npz     cv2.cornerMinEigenVal / cv2.goodFeaturesToTrack on the RGB2GRAY image of seeded frames
+                  (matcher.cpp:313 + :123-130), for the reference's parameters (120, 0.01, 20) and denser ones
 
 It also re-runs the arithmetic probes that fixed the oracle's operation order (see oracle.h) and
 prints what fraction of each cv2 primitive's output the oracle reproduces bit-for-bit.
@@ -116,6 +118,28 @@ def main():
     idx, dist = t0.hamming_knn2_cv2(q.view(np.uint8), t.view(np.uint8))
     print("hamming: %d queries with tied best distance" % int((dist[:, 0] == dist[:, 1]).sum()))
     np.savez_compressed(os.path.join(HERE, "hamming.npz"), q=q, t=t, idx=idx, dist=dist)
+    # corner seeding: response map and corner lists from the real OpenCV
+    out = {}
+    params = [(120, 0.01, 20.0), (2000, 0.01, 5.0), (500, 0.001, 3.5), (300, 0.05, 0.0)]
+    out["params"] = np.float64(params)
+    for name, (h, w, seed) in {"s": (96, 128, 3), "m": (240, 320, 4), "vga": (480, 640, 1)}.items():
+        fr = synth.make_frames(seed, 1, h, w).numpy()[0]
+        grey = cv2.cvtColor(fr, cv2.COLOR_RGB2GRAY)
+        eig = cv2.cornerMinEigenVal(grey, 3, ksize=3)
+        if name != "vga":
+            out[name + "_frame"] = fr
+            out[name + "_eig"] = eig
+        else:  # the VGA frame is regenerated from its seed; its gray image is stored as a checksum
+            out[name + "_seed"] = np.int64([seed, h, w])
+            out[name + "_gray_sum"] = np.int64(grey.astype(np.int64).sum())
+            out[name + "_eig_rows"] = eig[::40]
+        for k, (maxc, q, mind) in enumerate(params):
+            c = cv2.goodFeaturesToTrack(grey, maxc, q, mind)
+            out["%s_corners%d" % (name, k)] = c.reshape(-1, 2) if c is not None else np.zeros((0, 2), np.float32)
+        oc, oe, _ = po.good_features(fr, 120, 0.01, 20.0, want_eig=True)
+        print("goodFeaturesToTrack %dx%d: response map bit-exact: %s, corners identical: %s" % (
+            w, h, np.array_equal(oe.view(np.uint32), eig.view(np.uint32)), np.array_equal(oc, out[name + "_corners0"])))
+    np.savez_compressed(os.path.join(HERE, "corners.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-14s %7.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

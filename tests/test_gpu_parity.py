@@ -317,3 +317,32 @@ def test_config5_hamming_1m_x_1m_properties(fe, po, synth):
     rows = np.concatenate([planted[:64], rng.choice(n, 192, replace=False)])
     oi, od, oo = po.hamming256_top2(q[rows], t, 4, 5, 80)
     assert np.array_equal(idx[rows], oi) and np.array_equal(dist[rows], od) and np.array_equal(ok[rows], oo)
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (240, 320), (96, 83), (33, 48), (1080, 1920)])
+def test_good_features_bit_exact(fe, po, synth, shape):
+    """goodFeaturesToTrack (matcher.cpp:123-130) on the RGB2GRAY image: response map bit for bit, corner lists
+    identical (order included) for the reference's parameters and for denser settings."""
+    H, W = shape
+    frames = synth.make_frames(17 + H, 2, H, W).numpy()
+    for (maxc, q, mind) in ((120, 0.01, 20.0), (2000, 0.01, 5.0), (500, 0.001, 3.5), (300, 0.05, 0.0)):
+        corners, eig = fe.good_features(frames, maxc, q, mind, want_eig=True)
+        for f in range(2):
+            oc, oe, _ = po.good_features(frames[f], maxc, q, mind, want_eig=True)
+            assert_bits_equal(eig[f], oe, "response map %dx%d frame %d" % (W, H, f))
+            assert corners[f].shape == oc.shape and np.array_equal(corners[f], oc), (shape, maxc, q, mind, f, len(corners[f]), len(oc))
+
+
+def test_good_features_device_batch(fe, po, synth):
+    """Device-pointer variant on a batch; a flat (textureless) frame yields no corners."""
+    import torch
+    H, W = 240, 320
+    frames = synth.make_frames(3, 6, H, W)
+    frames[4] = 77
+    xy, cnt = fe.good_features(frames.cuda(), 120, 0.01, 20.0)
+    fe.sync()
+    xy, cnt = xy.cpu().numpy(), cnt.cpu().numpy()
+    for f in range(6):
+        oc = po.good_features(frames[f].numpy(), 120, 0.01, 20.0)
+        assert cnt[f] == len(oc) and np.array_equal(xy[f, :cnt[f]], oc), f
+    assert cnt[4] == 0

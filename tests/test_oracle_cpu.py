@@ -125,6 +125,31 @@ def test_hamming_vs_cv2_bfmatcher_golden(po):
     assert np.array_equal(ok.astype(bool), exp_ok)
 
 
+def test_good_features_vs_cv2_golden(po, synth):
+    """Corner seeding (matcher.cpp:313 + :123-130): the oracle's cornerMinEigenVal map equals OpenCV's bit for bit and
+    its goodFeaturesToTrack lists are identical (order included) for four parameter sets on three frames."""
+    g = np.load(os.path.join(GOLD, "corners.npz"))
+    params = g["params"]
+    for name in ("s", "m", "vga"):
+        if name == "vga":
+            seed, h, w = (int(v) for v in g["vga_seed"])
+            fr = synth.make_frames(seed, 1, h, w).numpy()[0]
+            assert int(po.gray_u8(fr).astype(np.int64).sum()) == int(g["vga_gray_sum"]), "synthetic frame generator changed"
+        else:
+            fr = g[name + "_frame"]
+        for k, (maxc, q, mind) in enumerate(params):
+            c, eig, _ = po.good_features(fr, int(maxc), float(q), float(mind), want_eig=True)
+            ref = g["%s_corners%d" % (name, k)]
+            assert c.shape == ref.shape and np.array_equal(c, ref), (name, k, len(c), len(ref))
+        if name == "vga":
+            assert np.array_equal(eig[::40].view(np.uint32), g["vga_eig_rows"].view(np.uint32))
+        else:
+            assert np.array_equal(eig.view(np.uint32), g[name + "_eig"].view(np.uint32))
+    # degenerate inputs: a flat image has no corners; a tiny one does not crash
+    assert len(po.good_features(np.full((32, 48, 3), 90, np.uint8), 50, 0.01, 5.0)) == 0
+    assert po.good_features(np.zeros((16, 16, 3), np.uint8), 5, 0.01, 1.0).shape == (0, 2)
+
+
 def test_hamming_edge_cases(po):
     q = np.zeros((3, 8), np.uint32)
     idx, dist, ok = po.hamming256_top2(q, np.zeros((0, 8), np.uint32))
