@@ -656,7 +656,7 @@ int gftt_run(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stri
                   "good_features launch: %s");
 }
 bool gftt_args_ok(int w, int h, size_t row_stride, int count, int max_corners, double quality, double min_distance) {
-  return w >= 16 && h >= 16 && row_stride >= (size_t)3 * w && count >= 0 && max_corners >= 1 && max_corners <= 24000 &&
+  return w >= 16 && h >= 16 && row_stride >= (size_t)3 * w && count >= 0 && max_corners >= 1 && max_corners <= 8192 &&
          quality > 0 && min_distance >= 0;
 }
 }  // namespace

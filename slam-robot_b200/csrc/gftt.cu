@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int EIG_USEFUL = 28;  // lanes 2..29; two lanes on each side cover Sobel (1) + box (1)
-constexpr int SEL_THREADS = 512;
+constexpr int SEL_THREADS = 1024;
 
 __device__ __forceinline__ unsigned order_code(float f) {  // monotone float -> unsigned
   const unsigned u = __float_as_uint(f);
@@ -147,27 +147,47 @@ struct NmsArgs {
   double quality;
 };
 
+constexpr int NMS_ROWS = 16;  // rows per thread: a CTA covers 256 columns x 16 rows
 __global__ void __launch_bounds__(256) gftt_nms_kernel(const NmsArgs a) {
+  __shared__ unsigned long long s_keys[256 * NMS_ROWS];  // a CTA's candidates, appended to the frame's list in one piece
+  __shared__ int s_n, s_base;
   const int frame = blockIdx.z;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x < 1 || y < 1 || x >= a.w - 1 || y >= a.h - 1) return;  // featureselect.cpp scans interior pixels only
-  const float* e = a.eig + ((size_t)frame * a.h + y) * a.w + x;
+  const int x = blockIdx.x * 256 + threadIdx.x, y0 = blockIdx.y * NMS_ROWS;
   const float thr = (float)((double)order_decode(a.max_code[frame]) * a.quality);  // threshold(THRESH_TOZERO), float compare
-  const float v = e[0];
-  if (!(v > thr)) return;
-  // dilate 3x3 of the thresholded map: neighbours at or below the threshold count as 0
-  float m = v;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const float n = e[dy * a.w + dx];
-      m = fmaxf(m, n > thr ? n : 0.f);
+  const bool xin = x >= 1 && x < a.w - 1;  // featureselect.cpp scans interior pixels only
+  const float* base = a.eig + (size_t)frame * a.h * a.w + min(max(x, 1), a.w - 2);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // thresholded 3-pixel row maxima of the rows above / at / below, carried down the column
+  auto tz = [&](float v) { return v > thr ? v : 0.f; };
+  auto rowmax = [&](int y, float& centre) {
+    const float* e = base + (size_t)y * a.w;
+    centre = e[0];
+    return fmaxf(fmaxf(tz(e[-1]), tz(centre)), tz(e[1]));
+  };
+  float c0, c1, c2;
+  float m0 = rowmax(max(y0 - 1, 0), c0), m1 = rowmax(min(y0, a.h - 1), c1);
+  for (int y = y0; y < min(y0 + NMS_ROWS, a.h - 1); ++y) {
+    const float m2 = rowmax(y + 1, c2);
+    const float v = c1;
+    // dilate 3x3 of the thresholded map: v is a candidate iff it survives the threshold and equals the local maximum
+    const bool cand = xin && y >= 1 && v > thr && v != 0.f && v == fmaxf(fmaxf(m0, m1), m2);
+    const unsigned peers = __ballot_sync(SFE_FULL, cand);
+    if (peers) {  // one shared-memory atomic per warp: the surviving lanes take consecutive slots
+      const int leader = __ffs(peers) - 1;
+      int slot0 = 0;
+      if (lane == leader) slot0 = atomicAdd(&s_n, __popc(peers));
+      slot0 = __shfl_sync(SFE_FULL, slot0, leader);
+      if (cand) s_keys[slot0 + __popc(peers & ((1u << lane) - 1))] = ((unsigned long long)order_code(v) << 32) | (unsigned)(y * a.w + x);
     }
-  if (v != m || v == 0.f) return;
-  const int slot = atomicAdd(a.ncand + frame, 1);
-  if (slot < a.cap)
-    a.keys[(size_t)frame * a.cap + slot] = ((unsigned long long)order_code(v) << 32) | (unsigned)(y * a.w + x);
+    m0 = m1; m1 = m2; c1 = c2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = s_n ? atomicAdd(a.ncand + frame, s_n) : 0;  // one global atomic per CTA
+  __syncthreads();
+  for (int i = threadIdx.x; i < s_n; i += 256)
+    if (s_base + i < a.cap) a.keys[(size_t)frame * a.cap + s_base + i] = s_keys[i];
 }
 
 struct SelArgs {
@@ -179,8 +199,28 @@ struct SelArgs {
   double min_distance;
 };
 
-// One CTA per frame.  Keys are sorted in place in global memory (the working set of a frame stays in L2).
+// One CTA per frame.  Bitonic sort, descending: stages whose partner distance is below SEL_CHUNK run on
+// chunks staged in shared memory (one load and one store per chunk and pass), the few wider ones in global
+// memory (a frame's keys stay in L2).
+constexpr int SEL_CHUNK = 16384;
+__device__ __forceinline__ void bitonic_chunk(unsigned long long* sk, int chunk_base, int len, int k_lo, int k_hi, int j_hi, int tid) {
+  // all stages (k, j) with k in [k_lo, k_hi] and j <= min(k/2, j_hi), on `len` keys whose global index starts at chunk_base
+  for (int k = k_lo; k <= k_hi; k <<= 1)
+    for (int j = min(k >> 1, j_hi); j > 0; j >>= 1) {
+      for (int t = tid; t < (len >> 1); t += SEL_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+        const unsigned long long ki = sk[i], kl = sk[l];
+        const bool desc = ((chunk_base + i) & k) == 0;
+        if (desc ? ki < kl : ki > kl) { sk[i] = kl; sk[l] = ki; }
+      }
+      __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) gftt_select_kernel(const SelArgs a) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  float* acc = reinterpret_cast<float*>(sel_smem);                                                    // [max_corners][2]
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(sel_smem + ((8 * (size_t)a.max_corners + 15) & ~(size_t)15));
   const int frame = blockIdx.x, tid = threadIdx.x;
   unsigned long long* keys = a.keys + (size_t)frame * a.cap;
   if (a.ncand[frame] > a.cap) {  // candidate list overflowed: report instead of returning a wrong list
@@ -192,22 +232,37 @@ __global__ void __launch_bounds__(SEL_THREADS) gftt_select_kernel(const SelArgs 
   while (np2 < n) np2 <<= 1;
   for (int i = n + tid; i < np2; i += SEL_THREADS) keys[i] = 0ull;  // pad: sorts to the end (descending)
   __syncthreads();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < np2; i += SEL_THREADS) {
-        const int l = i ^ j;
-        if (l > i) {
-          const unsigned long long ki = keys[i], kl = keys[l];
-          const bool desc = (i & k) == 0;
-          if (desc ? ki < kl : ki > kl) { keys[i] = kl; keys[l] = ki; }
-        }
+  const int chunk = min(np2, SEL_CHUNK);
+  // pass 1: every chunk fully sorted (alternating directions come from the global index)
+  for (int c0 = 0; c0 < np2; c0 += chunk) {
+    for (int i = tid; i < chunk; i += SEL_THREADS) sk[i] = keys[c0 + i];
+    __syncthreads();
+    bitonic_chunk(sk, c0, chunk, 2, chunk, chunk, tid);
+    for (int i = tid; i < chunk; i += SEL_THREADS) keys[c0 + i] = sk[i];
+    __syncthreads();
+  }
+  // wider merges: global steps while the partner distance spans chunks, then one shared-memory pass per chunk
+  for (int k = chunk << 1; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j >= chunk; j >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += SEL_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+        const unsigned long long ki = keys[i], kl = keys[l];
+        const bool desc = (i & k) == 0;
+        if (desc ? ki < kl : ki > kl) { keys[i] = kl; keys[l] = ki; }
       }
       __syncthreads();
     }
+    for (int c0 = 0; c0 < np2; c0 += chunk) {
+      for (int i = tid; i < chunk; i += SEL_THREADS) sk[i] = keys[c0 + i];
+      __syncthreads();
+      bitonic_chunk(sk, c0, chunk, k, k, chunk >> 1, tid);
+      for (int i = tid; i < chunk; i += SEL_THREADS) keys[c0 + i] = sk[i];
+      __syncthreads();
+    }
+  }
   // greedy selection (featureselect.cpp): a candidate is kept unless an accepted corner lies closer than
   // min_distance.  Sequential by nature; one warp walks the sorted candidates and tests each against the
   // accepted corners 32 at a time.
-  extern __shared__ float acc[];  // [max_corners][2]
   if (tid >= 32) return;
   float* out = a.corners + (size_t)frame * a.max_corners * 2;
   const bool check = a.min_distance >= 1.0;
@@ -248,12 +303,12 @@ int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_str
   EigArgs ea{bgr, row_stride, frame_stride, eig, max_code, w, h, (w + EIG_USEFUL - 1) / EIG_USEFUL};
   gftt_eig_kernel<<<ea.strips * count, 32, 0, s>>>(ea);
   NmsArgs na{eig, max_code, keys, ncand, w, h, cap, quality};
-  gftt_nms_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, count), 256, 0, s>>>(na);
+  gftt_nms_kernel<<<dim3((w + 255) / 256, (h + NMS_ROWS - 1) / NMS_ROWS, count), 256, 0, s>>>(na);
   SelArgs sa{keys, ncand, corners, ncorners, w, cap, max_corners, min_distance};
-  const size_t smem = sizeof(float) * 2 * (size_t)max_corners;
+  const size_t smem = ((sizeof(float) * 2 * (size_t)max_corners + 15) & ~(size_t)15) + sizeof(unsigned long long) * SEL_CHUNK;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gftt_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gftt_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
   gftt_select_kernel<<<count, SEL_THREADS, smem, s>>>(sa);

@@ -40,9 +40,20 @@
 
 namespace sfe {
 
-// goodFeaturesToTrack stays on the host for now (SURVEY.md 8f rank 1 "next"): the caller passes the
-// detector; it receives the BGR frame and returns candidate corners (matcher.cpp:125-130).
+// Corner seeding (matcher.cpp:313 + :125-130).  By default the GPU implementation of
+// cvtColor(RGB2GRAY) + goodFeaturesToTrack(grey, 120, 0.01, 20) is used (sfe_good_features, bit-identical
+// to OpenCV's corner lists); a caller may inject its own detector, which receives the BGR frame.
 typedef std::function<std::vector<Point2f>(const ImageView&)> CornerDetector;
+
+inline std::vector<Point2f> GpuGoodFeatures(const Context& ctx, const ImageView& bgr, int max_corners = 120,
+                                            double quality = 0.01, double min_distance = 20.0) {
+  std::vector<Point2f> out((size_t)max_corners);
+  int32_t n = 0;
+  ctx.check(sfe_good_features(ctx.get(), bgr.data, bgr.cols, bgr.rows, bgr.step, bgr.step * (size_t)bgr.rows, 1, max_corners,
+                              quality, min_distance, reinterpret_cast<float*>(out.data()), &n, nullptr));
+  out.resize((size_t)n);
+  return out;
+}
 
 template <class Frame, class LocalMap, class TrackedPoint, class Vec2>
 class MatcherT {
@@ -218,9 +229,8 @@ class MatcherT {
   // an existing match
   template <class Mat>
   void AddNewFeatures(const Mat& img, const std::map<Feature*, Point2f>& matches, std::vector<Point2f>* result) const {
-    if (!detector_) return;
     ImageView iv{(const uint8_t*)img.data, img.cols, img.rows, (size_t)img.step};
-    std::vector<Point2f> corners = detector_(iv);
+    std::vector<Point2f> corners = detector_ ? detector_(iv) : GpuGoodFeatures(*tracker_.context(), iv);  // :125-130
     int grid[kGrid + 2][kGrid + 2] = {};
     for (const auto& m : matches) {
       const Point2f& pt = m.second;
