@@ -224,6 +224,32 @@ int sfe_good_features_dev(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, si
                           size_t frame_stride, int count, int max_corners, double quality,
                           double min_distance, float* corners, int32_t* ncorners);
 
+/* ---- seeding the search (the step before tracking) ------------------------------------------ */
+
+/* Replaces the head of the FindMatches loop, matcher.cpp:224-245, for n features of one target frame:
+ *   levels[i]  = uncertainty[i] > 100 ? 6 : 3                                     (matcher.cpp:227-229)
+ *   seed_xy[i] = from_xy[i], or Frame::Project(point) (localmap.cpp:18-26 -> project.h:11-54) when
+ *                uncertainty[i] < 100 and the point projects                      (matcher.cpp:233-239)
+ *   go[i]      = 0 when the seed is out of bounds (`continue`, matcher.cpp:243), else 1
+ * points4 [n][4] homogeneous map points (TrackedPoint::location()), rot4 = the frame's rotation
+ * quaternion coefficients [x,y,z,w], trans3 its translation, k7 = Camera::k [k1,k2,k3,fx,fy,cx,cy]
+ * (localmap.h:28-30); cols/rows = size of the target frame.  The pose arguments are host arrays in
+ * both variants (call parameters). */
+int sfe_seed_features(sfe_ctx* ctx, int n, const double* points4, const double* uncertainty,
+                      const double* rot4, const double* trans3, const double* k7, const float* from_xy,
+                      int cols, int rows, float* seed_xy, int32_t* levels, uint8_t* go);
+int sfe_seed_features_dev(sfe_ctx* ctx, int n, const double* points4, const double* uncertainty,
+                          const double* rot4, const double* trans3, const double* k7,
+                          const float* from_xy, int cols, int rows, float* seed_xy, int32_t* levels,
+                          uint8_t* go);
+
+/* ---- live capture format --------------------------------------------------------------------- */
+
+/* Replaces the integer YUYV -> BGR loop of the V4L2 capture path, video.cpp:187-223: npixels pixels
+ * (a multiple of 4), 2 bytes per pixel in, 3 bytes per pixel out (the CV_8UC3 frame MakePyramid takes). */
+int sfe_yuyv_to_bgr(sfe_ctx* ctx, const uint8_t* yuyv_host, size_t npixels, uint8_t* bgr_host);
+int sfe_yuyv_to_bgr_dev(sfe_ctx* ctx, const uint8_t* yuyv_dev, size_t npixels, uint8_t* bgr_dev);
+
 #ifdef __cplusplus
 }
 #endif

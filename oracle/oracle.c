@@ -670,6 +670,69 @@ int orc_good_features(const uint8_t* bgr, int w, int h, size_t stride, int max_c
   return n;
 }
 
+/* ------------------------------------------------------------------ seeding the search */
+
+/* Frame::Project (localmap.cpp:18-26 -> project.h:11-54) in double, operation for operation; the quaternion
+ * product is Eigen 3.2's _transformVector: uv = 2*(q.vec x v); v + w*uv + q.vec x uv.  rot = [x,y,z,w].
+ * Returns 0 when the point is behind the lens (project.h:27). */
+int orc_project(const double* rot, const double* trans, const double* k, const double* pt, double* out2) {
+  const double vx = pt[0] - trans[0] * pt[3], vy = pt[1] - trans[1] * pt[3], vz = pt[2] - trans[2] * pt[3];
+  const double qx = rot[0], qy = rot[1], qz = rot[2], qw = rot[3];
+  double ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+  ux += ux; uy += uy; uz += uz;
+  const double px = (vx + qw * ux) + (qy * uz - qz * uy);
+  const double py = (vy + qw * uy) + (qz * ux - qx * uz);
+  const double pz = (vz + qw * uz) + (qx * uy - qy * ux);
+  if (pz < 0.001 * pt[3]) return 0;
+  double xp = px / pz, yp = py / pz;
+  const double r2 = xp * xp + yp * yp;
+  const double distort = 1.0 + r2 * (k[0] + r2 * (k[1] + r2 * k[2]));
+  xp *= distort; yp *= distort;
+  xp *= k[3]; yp *= k[4];
+  xp += k[5]; yp += k[6];
+  out2[0] = xp; out2[1] = yp;
+  return 1;
+}
+
+/* The per-feature head of the FindMatches loop (matcher.cpp:224-245): levels = uncertainty > 100 ? 6 : 3; the seed is
+ * from_pt, or the projection of the map point when uncertainty < 100 and it projects; go = 0 when the seed is out of
+ * bounds (note `>` on y, :243, preserved). */
+void orc_seed_features(int n, const double* points4, const double* uncertainty, const double* rot, const double* trans,
+                       const double* k, const float* from_xy, int cols, int rows, float* seed_xy, int32_t* levels,
+                       uint8_t* go) {
+  for (int i = 0; i < n; ++i) {
+    float x = from_xy[2 * i], y = from_xy[2 * i + 1];
+    levels[i] = uncertainty[i] > 100 ? 6 : 3;
+    double p[2];
+    if (uncertainty[i] < 100 && orc_project(rot, trans, k, points4 + 4 * i, p)) { x = (float)p[0]; y = (float)p[1]; }
+    seed_xy[2 * i] = x; seed_xy[2 * i + 1] = y;
+    go[i] = !(x < 0 || y < 0 || x >= (float)cols || y > (float)rows);
+  }
+}
+
+/* ------------------------------------------------------------------ live capture format */
+
+/* The integer YUYV -> BGR conversion of the V4L2 capture path, video.cpp:187-223: `bytes` of YUYV (4 bytes = 2 pixels)
+ * to 3 bytes per pixel. */
+void orc_yuyv_to_bgr(const uint8_t* in, size_t bytes, uint8_t* out) {
+#define ORC_SAT(c) if ((c) & (~255)) { if ((c) < 0) (c) = 0; else (c) = 255; }
+  for (size_t i = 0; i + 3 < bytes; i += 4, in += 4) {
+    int y1 = in[0];
+    int cb = ((in[1] - 128) * 454) >> 8;
+    int cg = (in[1] - 128) * 88;
+    int y2 = in[2];
+    int cr = ((in[3] - 128) * 359) >> 8;
+    cg = (cg + (in[3] - 128) * 183) >> 8;
+    int r = y1 + cr, b = y1 + cb, g = y1 - cg;
+    ORC_SAT(r); ORC_SAT(g); ORC_SAT(b);
+    *out++ = (uint8_t)b; *out++ = (uint8_t)g; *out++ = (uint8_t)r;
+    r = y2 + cr; b = y2 + cb; g = y2 - cg;
+    ORC_SAT(r); ORC_SAT(g); ORC_SAT(b);
+    *out++ = (uint8_t)b; *out++ = (uint8_t)g; *out++ = (uint8_t)r;
+  }
+#undef ORC_SAT
+}
+
 /* ------------------------------------------------------------------ P2 KLTTracker */
 
 /* klt.h:59-96: three full 13x13 getRectSubPix calls, no edge clipping. */

@@ -134,6 +134,14 @@ int orc_brute_track(const orc_pyr* from, const orc_pyr* to, int n, const float* 
                     int n_fine, int* status, float* best_sad, int64_t* npos, int nthreads);
 
 /* ---- P4: Hamming ----------------------------------------------------------- */
+/* Seeding (8f rank 3): Frame::Project (localmap.cpp:18-26, project.h:11-54) and the head of the FindMatches loop
+ * (matcher.cpp:224-245).  Live capture (8f rank 4): the integer YUYV -> BGR conversion of video.cpp:187-223. */
+int orc_project(const double* rot, const double* trans, const double* k, const double* pt, double* out2);
+void orc_seed_features(int n, const double* points4, const double* uncertainty, const double* rot, const double* trans,
+                       const double* k, const float* from_xy, int cols, int rows, float* seed_xy, int32_t* levels,
+                       uint8_t* go);
+void orc_yuyv_to_bgr(const uint8_t* in, size_t bytes, uint8_t* out);
+
 /* Corner seeding: cv::cornerMinEigenVal(gray8, 3, 3) and cv::goodFeaturesToTrack with
  * its defaults, as matcher.cpp:123-130 calls them; probed bit-for-bit against cv2 4.13 (see oracle.c). */
 void orc_min_eigen_val(const uint8_t* gray, int w, int h, float* eig);

@@ -92,6 +92,10 @@ def lib(fast=False, native=False):
     L.orc_brute_track.argtypes = [vp, vp, C.c_int, f32p, f32p, f32p, C.c_int, f32p, C.c_int, i32p, f32p, i64p,
                                   C.c_int]
     L.orc_brute_track.restype = C.c_int
+    f64p = C.POINTER(C.c_double)
+    L.orc_project.argtypes = [f64p, f64p, f64p, f64p, f64p]
+    L.orc_seed_features.argtypes = [C.c_int, f64p, f64p, f64p, f64p, f64p, f32p, C.c_int, C.c_int, f32p, i32p, u8p]
+    L.orc_yuyv_to_bgr.argtypes = [u8p, C.c_size_t, u8p]
     L.orc_min_eigen_val.argtypes = [u8p, C.c_int, C.c_int, f32p]
     L.orc_good_features.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, f32p, f32p, f32p]
     L.orc_hamming256_top2.argtypes = [u32p, C.c_int, u32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, u8p,
@@ -322,3 +326,27 @@ def good_features(bgr, max_corners=120, quality=0.01, min_distance=20.0, want_ei
     n = lib().orc_good_features(_p(bgr, C.c_uint8), w, h, bgr.strides[0], max_corners, float(quality), float(min_distance),
                                 _p(xy, C.c_float), _p(eig, C.c_float), _p(mx, C.c_float))
     return (xy[:n].copy(), eig, float(mx[0])) if want_eig else xy[:n].copy()
+
+
+def seed_features(points4, uncertainty, rot, trans, k, from_xy, cols, rows):
+    """matcher.cpp:224-245 for n features: (seed_xy, levels, go)."""
+    pts = np.ascontiguousarray(points4, np.float64).reshape(-1, 4)
+    n = len(pts)
+    unc = np.ascontiguousarray(uncertainty, np.float64)
+    rot, trans, k = (np.ascontiguousarray(a, np.float64) for a in (rot, trans, k))
+    fxy = _f32(from_xy).reshape(-1, 2)
+    seed = np.empty((n, 2), np.float32)
+    lv = np.empty(n, np.int32)
+    go = np.empty(n, np.uint8)
+    lib().orc_seed_features(n, _p(pts, C.c_double), _p(unc, C.c_double), _p(rot, C.c_double), _p(trans, C.c_double),
+                            _p(k, C.c_double), _p(fxy, C.c_float), int(cols), int(rows), _p(seed, C.c_float),
+                            _p(lv, C.c_int32), _p(go, C.c_uint8))
+    return seed, lv, go
+
+
+def yuyv_to_bgr(yuyv):
+    """video.cpp:187-223 on a flat uint8 YUYV buffer (2 bytes per pixel) -> flat BGR (3 bytes per pixel)."""
+    yuyv = np.ascontiguousarray(yuyv, np.uint8).ravel()
+    out = np.empty(yuyv.size // 4 * 6, np.uint8)
+    lib().orc_yuyv_to_bgr(_p(yuyv, C.c_uint8), yuyv.size, _p(out, C.c_uint8))
+    return out

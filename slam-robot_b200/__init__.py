@@ -33,6 +33,7 @@ EXPORTS = [
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
     "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_good_features", "sfe_good_features_dev",
+    "sfe_seed_features", "sfe_seed_features_dev", "sfe_yuyv_to_bgr", "sfe_yuyv_to_bgr_dev",
 ]
 
 
@@ -113,6 +114,11 @@ def lib():
     L.sfe_match_hamming256_async.argtypes = ham
     L.sfe_good_features.argtypes = [vp, vp, i32, i32, sz, sz, i32, i32, C.c_double, C.c_double, vp, vp, vp]
     L.sfe_good_features_dev.argtypes = [vp, vp, i32, i32, sz, sz, i32, i32, C.c_double, C.c_double, vp, vp]
+    seed = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.sfe_seed_features.argtypes = seed
+    L.sfe_seed_features_dev.argtypes = seed
+    L.sfe_yuyv_to_bgr.argtypes = [vp, vp, sz, vp]
+    L.sfe_yuyv_to_bgr_dev.argtypes = [vp, vp, sz, vp]
     L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
                                    vp, vp, i32]
     _lib = L
@@ -361,6 +367,25 @@ class FrontEnd:
                                            float(min_distance), _ptr(xy), _ptr(cnt), _ptr(eig)))
         corners = [xy[i, :cnt[i]].copy() for i in range(n)]
         return (corners, eig) if want_eig else corners
+
+    # ---- seeding the search (matcher.cpp:224-245) and the live capture format (video.cpp:187-223)
+    def seed_features(self, points4, uncertainty, rot4, trans3, k7, from_xy, cols, rows):
+        pts = np.ascontiguousarray(points4, np.float64).reshape(-1, 4)
+        n = len(pts)
+        unc = np.ascontiguousarray(uncertainty, np.float64)
+        rot4, trans3, k7 = (np.ascontiguousarray(a, np.float64) for a in (rot4, trans3, k7))
+        fxy = _np(from_xy, np.float32).reshape(-1, 2)
+        seed, lv, go = np.empty((n, 2), np.float32), np.empty(n, np.int32), np.empty(n, np.uint8)
+        self._chk(self.L.sfe_seed_features(self.h, n, _ptr(pts), _ptr(unc), _ptr(rot4), _ptr(trans3), _ptr(k7), _ptr(fxy),
+                                           int(cols), int(rows), _ptr(seed), _ptr(lv), _ptr(go)))
+        return seed, lv, go
+
+    def yuyv_to_bgr(self, yuyv):
+        yuyv = np.ascontiguousarray(yuyv, np.uint8).ravel()
+        npx = yuyv.size // 2
+        out = np.empty(3 * npx, np.uint8)
+        self._chk(self.L.sfe_yuyv_to_bgr(self.h, _ptr(yuyv), npx, _ptr(out)))
+        return out
 
     def pinned(self, shape, dtype):
         """A page-locked host array (sfe_host_alloc): lets the host-pointer entry points copy asynchronously."""

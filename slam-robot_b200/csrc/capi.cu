@@ -705,4 +705,73 @@ int sfe_good_features(sfe_ctx* ctx, const uint8_t* bgr_host, int w, int h, size_
   return SFE_SUCCESS;
 }
 
+/* ---- seeding the search and the live capture format ---------------- */
+
+int sfe_seed_features_dev(sfe_ctx* ctx, int n, const double* points4, const double* uncertainty, const double* rot4,
+                          const double* trans3, const double* k7, const float* from_xy, int cols, int rows, float* seed_xy,
+                          int32_t* levels, uint8_t* go) {
+  if (!ctx || n < 0 || !rot4 || !trans3 || !k7 || (n && (!points4 || !uncertainty || !from_xy || !seed_xy || !levels || !go)))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad seed_features arguments");
+  if (n == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return launched(ctx, launch_seed_features(n, points4, uncertainty, rot4, trans3, k7, from_xy, cols, rows, seed_xy, levels, go,
+                                            ctx->stream), "seed_features launch: %s");
+}
+
+int sfe_seed_features(sfe_ctx* ctx, int n, const double* points4, const double* uncertainty, const double* rot4,
+                      const double* trans3, const double* k7, const float* from_xy, int cols, int rows, float* seed_xy,
+                      int32_t* levels, uint8_t* go) {
+  if (!ctx || n < 0 || !rot4 || !trans3 || !k7 || (n && (!points4 || !uncertainty || !from_xy || !seed_xy || !levels || !go)))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad seed_features arguments");
+  if (n == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  const size_t need = padded(32 * (size_t)n) + padded(8 * (size_t)n) * 3 + padded(4 * (size_t)n) + padded(n);
+  int rc = ensure_scratch(ctx, need);
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  double* d_pt = c.take<double>(4 * (size_t)n);
+  double* d_unc = c.take<double>(n);
+  float* d_from = c.take<float>(2 * (size_t)n);
+  float* d_seed = c.take<float>(2 * (size_t)n);
+  int32_t* d_lv = c.take<int32_t>(n);
+  uint8_t* d_go = c.take<uint8_t>(n);
+  cudaStream_t s = ctx->stream;
+  CU(cudaMemcpyAsync(d_pt, points4, 32 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_unc, uncertainty, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_from, from_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = sfe_seed_features_dev(ctx, n, d_pt, d_unc, rot4, trans3, k7, d_from, cols, rows, d_seed, d_lv, d_go);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(seed_xy, d_seed, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(levels, d_lv, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(go, d_go, (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SFE_SUCCESS;
+}
+
+int sfe_yuyv_to_bgr_dev(sfe_ctx* ctx, const uint8_t* yuyv, size_t npixels, uint8_t* bgr) {
+  if (!ctx || (npixels && (!yuyv || !bgr)) || npixels % 4 || ((uintptr_t)yuyv & 7) || ((uintptr_t)bgr & 3))
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad yuyv_to_bgr arguments (pixel count must be a multiple of 4, buffers 8/4-byte aligned)");
+  if (npixels == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  return launched(ctx, launch_yuyv_to_bgr(yuyv, npixels, bgr, ctx->stream), "yuyv_to_bgr launch: %s");
+}
+
+int sfe_yuyv_to_bgr(sfe_ctx* ctx, const uint8_t* yuyv, size_t npixels, uint8_t* bgr) {
+  if (!ctx || (npixels && (!yuyv || !bgr)) || npixels % 4)
+    return fail(ctx, SFE_ERR_INVALID, "%s", "bad yuyv_to_bgr arguments (pixel count must be a multiple of 4)");
+  if (npixels == 0) return SFE_SUCCESS;
+  if (use_device(ctx)) return SFE_ERR_CUDA;
+  int rc = ensure_scratch(ctx, padded(2 * npixels) + padded(3 * npixels));
+  if (rc) return rc;
+  Carver c{(char*)ctx->scratch, 0};
+  uint8_t* d_in = c.take<uint8_t>(2 * npixels);
+  uint8_t* d_out = c.take<uint8_t>(3 * npixels);
+  CU(cudaMemcpyAsync(d_in, yuyv, 2 * npixels, cudaMemcpyHostToDevice, ctx->stream));
+  rc = sfe_yuyv_to_bgr_dev(ctx, d_in, npixels, d_out);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(bgr, d_out, 3 * npixels, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SFE_SUCCESS;
+}
+
 }  // extern "C"

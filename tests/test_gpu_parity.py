@@ -346,3 +346,35 @@ def test_good_features_device_batch(fe, po, synth):
         oc = po.good_features(frames[f].numpy(), 120, 0.01, 20.0)
         assert cnt[f] == len(oc) and np.array_equal(xy[f, :cnt[f]], oc), f
     assert cnt[4] == 0
+
+
+def test_seed_features_bit_exact(fe, po):
+    """Head of the FindMatches loop (matcher.cpp:224-245): levels from the uncertainty, Frame::Project seeds
+    (project.h:11-54, doubles) and the out-of-bounds gate -- incl. points behind the lens and on the bounds."""
+    rng = np.random.default_rng(9)
+    n = 5000
+    ang = 0.3
+    axis = np.float64([0.2, -0.5, 0.1]); axis /= np.linalg.norm(axis)
+    rot = np.concatenate([axis * np.sin(ang / 2), [np.cos(ang / 2)]])
+    trans = np.float64([0.3, -0.1, 0.5])
+    k = np.float64([-0.12, 0.03, -0.004, 310.0, 305.0, 322.5, 238.25])
+    pts = np.concatenate([rng.normal(0, 3, (n, 2)), rng.uniform(-2, 12, (n, 1)), rng.uniform(0.5, 2, (n, 1))], 1)
+    unc = rng.choice([1e8, 150.0, 100.0, 99.0, 3.0], n)
+    from_xy = np.stack([rng.uniform(-5, 650, n), rng.uniform(-5, 490, n)], 1).astype(np.float32)
+    from_xy[:4] = [[0, 0], [640, 100], [100, 480], [639.99, 479.99]]
+    unc[:4] = 1e8
+    gs, gl, gg = fe.seed_features(pts, unc, rot, trans, k, from_xy, 640, 480)
+    os_, ol, og = po.seed_features(pts, unc, rot, trans, k, from_xy, 640, 480)
+    assert_bits_equal(gs, os_, "seeds")
+    assert np.array_equal(gl, ol) and np.array_equal(gg, og)
+    assert set(np.unique(gl)) == {3, 6} and 0 < gg.mean() < 1
+    assert list(gg[:4]) == [1, 0, 1, 1]   # x >= cols is out, y == rows is still in (matcher.cpp:243 uses `>` on y)
+
+
+def test_yuyv_to_bgr_bit_exact(fe, po):
+    """video.cpp:187-223 on a random VGA buffer plus the saturating corners of the colour cube."""
+    rng = np.random.default_rng(2)
+    buf = rng.integers(0, 256, 640 * 480 * 2, dtype=np.uint8)
+    buf[:16] = [0, 0, 0, 0, 255, 255, 255, 255, 255, 0, 255, 0, 0, 255, 0, 255]
+    assert np.array_equal(fe.yuyv_to_bgr(buf), po.yuyv_to_bgr(buf))
+    assert fe.yuyv_to_bgr(np.zeros(0, np.uint8)).size == 0

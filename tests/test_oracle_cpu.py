@@ -150,6 +150,46 @@ def test_good_features_vs_cv2_golden(po, synth):
     assert po.good_features(np.zeros((16, 16, 3), np.uint8), 5, 0.01, 1.0).shape == (0, 2)
 
 
+def test_seed_and_yuyv_oracles_against_independent_restatements(po):
+    """8f ranks 3 and 4 have no OpenCV inside: the oracle follows project.h:11-54 / video.cpp:187-223 line by line
+    (Eigen itself is absent here, so the quaternion product's operation order is stated from Eigen 3.2 and
+    "parity unpinned" to the last bit); checked against independent numpy formulations."""
+    rng = np.random.default_rng(4)
+    n = 2000
+    axis = np.float64([0.1, 0.7, -0.2]); axis /= np.linalg.norm(axis)
+    ang = -0.4
+    rot = np.concatenate([axis * np.sin(ang / 2), [np.cos(ang / 2)]])
+    trans = np.float64([0.2, 0.1, -0.3])
+    k = np.float64([-0.1, 0.02, 0.001, 300.0, 301.0, 320.0, 240.0])
+    pts = np.concatenate([rng.normal(0, 2, (n, 2)), rng.uniform(1, 10, (n, 1)), rng.uniform(0.5, 2, (n, 1))], 1)
+    from_xy = rng.uniform(0, 400, (n, 2)).astype(np.float32)
+    seed, lv, go = po.seed_features(pts, np.full(n, 5.0), rot, trans, k, from_xy, 640, 480)
+    # rotation matrix form of the same projection
+    x, y, z, w = rot
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    p = (R @ (pts[:, :3] - trans * pts[:, 3:4]).T).T
+    xp, yp = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+    r2 = xp * xp + yp * yp
+    d = 1 + r2 * (k[0] + r2 * (k[1] + r2 * k[2]))
+    ref = np.stack([xp * d * k[3] + k[5], yp * d * k[4] + k[6]], 1)
+    ok = p[:, 2] >= 0.001 * pts[:, 3]
+    assert ok.all() and np.allclose(seed, ref.astype(np.float32), rtol=0, atol=2e-3 * np.maximum(1, np.abs(ref)).max() * 1e-3 + 1e-3)
+    assert (lv == 3).all()
+    assert np.array_equal(go.astype(bool), ~((seed[:, 0] < 0) | (seed[:, 1] < 0) | (seed[:, 0] >= 640) | (seed[:, 1] > 480)))
+    # uncertainty >= 100: the seed stays from_pt, levels 6 above 100
+    s2, l2, _ = po.seed_features(pts, np.where(np.arange(n) % 2, 100.0, 1e8), rot, trans, k, from_xy, 640, 480)
+    assert np.array_equal(s2, from_xy) and set(l2[::2]) == {6} and set(l2[1::2]) == {3}
+    # YUYV: vectorised numpy restatement
+    buf = rng.integers(0, 256, 4 * 5000, dtype=np.uint8)
+    q = buf.reshape(-1, 4).astype(np.int64)
+    u, v = q[:, 1] - 128, q[:, 3] - 128
+    cb, cr, cg = (u * 454) >> 8, (v * 359) >> 8, (u * 88 + v * 183) >> 8
+    px = np.stack([q[:, 0] + cb, q[:, 0] - cg, q[:, 0] + cr, q[:, 2] + cb, q[:, 2] - cg, q[:, 2] + cr], 1).clip(0, 255).astype(np.uint8)
+    assert np.array_equal(po.yuyv_to_bgr(buf), px.ravel())
+
+
 def test_hamming_edge_cases(po):
     q = np.zeros((3, 8), np.uint32)
     idx, dist, ok = po.hamming256_top2(q, np.zeros((0, 8), np.uint32))
