@@ -175,7 +175,9 @@ def test_seed_and_yuyv_oracles_against_independent_restatements(po):
     d = 1 + r2 * (k[0] + r2 * (k[1] + r2 * k[2]))
     ref = np.stack([xp * d * k[3] + k[5], yp * d * k[4] + k[6]], 1)
     ok = p[:, 2] >= 0.001 * pts[:, 3]
-    assert ok.all() and np.allclose(seed, ref.astype(np.float32), rtol=0, atol=2e-3 * np.maximum(1, np.abs(ref)).max() * 1e-3 + 1e-3)
+    assert ok.sum() > n // 2 and (~ok).sum() > 0          # both branches of project.h:27 are exercised
+    assert np.allclose(seed[ok], ref[ok].astype(np.float32), rtol=1e-5, atol=1e-3)
+    assert np.array_equal(seed[~ok], from_xy[~ok])        # behind the lens: the seed stays from_pt
     assert (lv == 3).all()
     assert np.array_equal(go.astype(bool), ~((seed[:, 0] < 0) | (seed[:, 1] < 0) | (seed[:, 0] >= 640) | (seed[:, 1] > 480)))
     # uncertainty >= 100: the seed stays from_pt, levels 6 above 100
