@@ -3,7 +3,8 @@
 //
 // Host buffers in, host buffers out.  The pairs are cut into chunks; three CUDA streams form a pipeline
 //   copy stream     H2D of the BGR frames of chunk k+1 (double-buffered device staging)
-//   compute stream  MakePyramid of both frames + forward/backward tracking of chunk k (the context's stream)
+//   compute streams MakePyramid of both frames + forward/backward tracking of chunk k; chunks alternate between
+//                   two streams so that the next chunk's kernels fill the SMs the persistent tracker's tail frees
 //   output stream   D2H of the results of chunk k-1
 // ordered by events only, so with pinned host buffers (sfe_host_alloc) the PCIe traffic of a step hides
 // behind its kernels.  Staging buffers, pyramids and events are cached in the context between calls.
@@ -14,7 +15,7 @@
 #include "ctx.cuh"
 
 struct sfe_replay {
-  cudaStream_t copy_stream, out_stream;
+  cudaStream_t copy_stream, out_stream, compute2;  // compute alternates between the context's stream and compute2
   cudaEvent_t copied[2], consumed[2], tracked[2], drained;
   int w, h, depth, chunk;  // geometry the frame buffers / pyramids were built for
   uint8_t* d_frames[2];    // per buffer: `chunk` from-frames followed by `chunk` to-frames
@@ -70,6 +71,7 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
     ctx->replay = r;
     RCU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
     RCU(cudaStreamCreateWithFlags(&r->out_stream, cudaStreamNonBlocking));
+    RCU(cudaStreamCreateWithFlags(&r->compute2, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
       RCU(cudaEventCreateWithFlags(&r->copied[b], cudaEventDisableTiming));
       RCU(cudaEventCreateWithFlags(&r->consumed[b], cudaEventDisableTiming));
@@ -136,6 +138,7 @@ void sfe_replay_release(sfe_ctx* ctx) {
   if (r->drained) cudaEventDestroy(r->drained);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   if (r->out_stream) cudaStreamDestroy(r->out_stream);
+  if (r->compute2) cudaStreamDestroy(r->compute2);
   delete r;
   ctx->replay = nullptr;
 }
@@ -151,31 +154,34 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
       !from_xy || !to_xy || default_levels < 1 || maxit < 0 || row_stride < (size_t)3 * w)
     return rfail(ctx, SFE_ERR_INVALID, "bad arguments", cudaSuccess);
   RCU(cudaSetDevice(ctx->device));
-  // chunk size: default = an eighth of the batch (the first chunk's upload and the last chunk's download are
-  // the only exposed transfers), at least 8 pairs so that the kernels still fill the GPU
+  // chunk size: default = an eighth of the batch (at least 8 pairs so that the kernels still fill the GPU; measured
+  // best on B200 for 128 VGA pairs); the first chunk is a quarter of that, so compute starts after a short upload
   int chunk = chunk_pairs > 0 ? chunk_pairs : (npairs + 7) / 8;
   if (chunk_pairs <= 0 && chunk < 8) chunk = 8;
   if (chunk > npairs) chunk = npairs;
+  const int first_chunk = chunk >= 16 ? chunk / 4 : chunk;
   const size_t n = (size_t)npairs * n_per_pair;
   int rc = ensure(ctx, w, h, depth, chunk, n);
   if (rc) return rc;
   sfe_replay* r = ctx->replay;
-  cudaStream_t cs = ctx->stream, xs = r->copy_stream, os = r->out_stream;
+  cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream;
 
   // the feature lists are small: upload them in one piece ahead of the pipeline
-  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs));
-  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs));
-  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs));
-  // the copy and output streams must not run ahead of whatever the caller queued on the context's stream
-  // before this call, nor reuse the staging buffers of a previous call that is still in flight
-  RCU(cudaEventRecord(r->drained, cs));
+  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
+  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
+  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs0));
+  // the other streams must not run ahead of whatever the caller queued on the context's stream before this call
+  // (which also covers the staging buffers of a previous call)
+  RCU(cudaEventRecord(r->drained, cs0));
   RCU(cudaStreamWaitEvent(xs, r->drained, 0));
   RCU(cudaStreamWaitEvent(os, r->drained, 0));
+  RCU(cudaStreamWaitEvent(r->compute2, r->drained, 0));
 
   const size_t dense_frame = (size_t)3 * w * h;
-  const int nchunks = (npairs + chunk - 1) / chunk;
-  for (int k = 0; k < nchunks; ++k) {
-    const int b = k & 1, p0 = k * chunk, c = npairs - p0 < chunk ? npairs - p0 : chunk;
+  int p0 = 0;
+  for (int k = 0; p0 < npairs; ++k) {
+    const int b = k & 1, want = k == 0 ? first_chunk : chunk, c = npairs - p0 < want ? npairs - p0 : want;
+    cudaStream_t cs = b ? r->compute2 : cs0;
     // ---- copy stream: frames of chunk k into staging buffer b (free once chunk k-2's pyramids are built)
     if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
     rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride, c, xs);
@@ -184,18 +190,26 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
                          row_stride, frame_stride, c, xs);
     if (rc) return rc;
     RCU(cudaEventRecord(r->copied[b], xs));
-    // ---- compute stream: both pyramids, then forward/backward tracking of the chunk's features
+    // ---- compute stream b: both pyramids, then forward/backward tracking of the chunk's features.  Stream order
+    // protects pyramid set b (chunk k-2 used the same stream); the work-queue counter is per stream.
     RCU(cudaStreamWaitEvent(cs, r->copied[b], 0));
-    rc = sfe_pyr_build_dev(ctx, r->pyr_from[b], r->d_frames[b], (size_t)3 * w, dense_frame, 0, c);
-    if (!rc) rc = sfe_pyr_build_dev(ctx, r->pyr_to[b], r->d_frames[b] + (size_t)chunk * dense_frame, (size_t)3 * w, dense_frame, 0, c);
-    if (rc) return rc;
+    int nl = launch_pyr_build(r->pyr_from[b]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, c, cs);
+    if (nl >= 0) {
+      ctx->launches += nl;
+      nl = launch_pyr_build(r->pyr_to[b]->view, SFE_HESSIAN, r->d_frames[b] + (size_t)chunk * dense_frame, (size_t)3 * w,
+                            dense_frame, 0, c, cs);
+    }
+    if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "pyramid launch", (cudaError_t)(-nl));
+    ctx->launches += nl;
     RCU(cudaEventRecord(r->consumed[b], cs));
     const size_t f0 = (size_t)p0 * n_per_pair;
     const int nf = c * n_per_pair;
-    rc = sfe_track_fb_dev(ctx, r->pyr_from[b], 0, r->pyr_to[b], 0, nf, n_per_pair, r->d_from + 2 * f0, r->d_to + 2 * f0,
-                          levels ? r->d_lv + f0 : nullptr, default_levels, thr, maxit, fb_max, r->d_back + 2 * f0,
-                          r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0);
-    if (rc) return rc;
+    TrackArgs ta{nf, n_per_pair, 0, 0, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
+                 thr, maxit, fb_max, r->d_back + 2 * f0, r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0, 2};
+    nl = launch_track_hessian(r->pyr_from[b]->view, r->pyr_to[b]->view, ta, ctx->d_mask, ctx->d_counter + 16 * (1 + b),
+                              ctx->num_sms, cs);
+    if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "track launch", (cudaError_t)(-nl));
+    ctx->launches += nl;
     RCU(cudaEventRecord(r->tracked[b], cs));
     // ---- output stream: results of chunk k back to the caller's buffers
     RCU(cudaStreamWaitEvent(os, r->tracked[b], 0));
@@ -205,7 +219,9 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
     if (status_bwd) RCU(cudaMemcpyAsync(status_bwd + f0, r->d_s2 + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (accepted) RCU(cudaMemcpyAsync(accepted + f0, r->d_acc + f0, (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (steps) RCU(cudaMemcpyAsync(steps + f0, r->d_steps + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    p0 += c;
   }
+  cudaStream_t cs = cs0;
   // join: the context's stream is complete only when the last download is
   RCU(cudaEventRecord(r->drained, os));
   RCU(cudaStreamWaitEvent(cs, r->drained, 0));
