@@ -175,7 +175,19 @@ class FrontEnd:
             raise SlamFEError("libslamfe error %d: %s" % (rc, self.L.sfe_last_error(self.h).decode()))
 
     def set_stream(self, cuda_stream_ptr):
-        self._chk(self.L.sfe_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+        """None -> the context's own (non-blocking) stream; a cudaStream_t value -> that stream.  0 is CUDA's legacy
+        default stream (what torch.cuda.current_stream().cuda_stream returns unless a stream context is active): it is
+        passed as the explicit handle cudaStreamLegacy (0x1), because a NULL pointer means "own stream" in the C ABI."""
+        if cuda_stream_ptr is None:
+            ptr = 0
+        else:
+            ptr = int(cuda_stream_ptr) or 0x1
+        self._chk(self.L.sfe_set_stream(self.h, C.c_void_p(ptr)))
+
+    def use_torch_stream(self):
+        """Enqueue on torch's current stream, so kernels are ordered with torch ops and NCCL collectives."""
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sync(self):
         self._chk(self.L.sfe_sync(self.h))

@@ -43,7 +43,9 @@ def gather_rows(local, n_total, group=None):
 def match_hamming256_sharded(match_fn, q_all_or_local, t, nq_total, train_src=0, group=None, q_is_local=False):
     """Sharded brute-force Hamming top-2 (BASELINE config 5).
 
-    match_fn(q_rows, t_rows) -> (idx[m,2], dist[m,2], pass[m]) as torch tensors on q_rows.device.
+    match_fn(q_rows, t_rows) -> (idx[m,2], dist[m,2], pass[m]) as torch tensors on q_rows.device; it must enqueue
+    on torch's current stream (FrontEnd.use_torch_stream()), which is what orders it after the broadcast and before
+    the all-gather.
     q_all_or_local: either the full query set (every rank slices its own block) or, with
     q_is_local=True, this rank's block.  t: the train set; only rank `train_src`'s copy is used
     (it is broadcast, i.e. replicated over NVLink).  Returns the gathered (idx, dist, pass) for all
