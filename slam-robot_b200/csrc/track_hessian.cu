@@ -172,6 +172,31 @@ __device__ __forceinline__ double div_h(double x) {
   return __fma_rn(r, y, q);
 }
 
+// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE single-precision operations per instruction, each rounded
+// exactly like its scalar form).  The kernel is bound by instruction issue, not by the FMA pipe, so the element-wise
+// work of the six candidate patches is done on PAIRS OF SHIFTS: .x = shift 2p, .y = shift 2p+1.  A scalar operand is
+// written {s, s}; ptxas turns that into the instruction's broadcast form, no move is issued.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 both(float s) { return make_float2(s, s); }
+
 // Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
 // returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
 __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
@@ -281,7 +306,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
 
   // ---- sampling + patch statistics of the six candidates (hessian.h:85-91): 12 partial sums per lane
   float st[16];
-  float v[6][SFE_SLOTS];
+  float2 v[3][SFE_SLOTS];  // candidate patch values, shifts paired: v[p][k] = (shift 2p, shift 2p+1) of slot k
   if (fast) {
     // every patch pixel reads its 4 taps once; six weight sets
     float ax[3], ax1[3], ay[3], ay1[3];
@@ -305,28 +330,33 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
       t11[k] = tp[TS + 1];
     }
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
-      const float w0 = ax1[jx] * ay1[jy], w1 = ax[jx] * ay1[jy], w2 = ax1[jx] * ay[jy], w3 = ax[jx] * ay[jy];
+    for (int p = 0; p < 3; ++p) {
+      const int jxa = (SXP >> (4 * p)) & 3, jya = (SYP >> (4 * p)) & 3, jxb = (SXP >> (4 * p + 2)) & 3, jyb = (SYP >> (4 * p + 2)) & 3;
+      const float2 w0 = make_float2(ax1[jxa] * ay1[jya], ax1[jxb] * ay1[jyb]), w1 = make_float2(ax[jxa] * ay1[jya], ax[jxb] * ay1[jyb]);
+      const float2 w2 = make_float2(ax1[jxa] * ay[jya], ax1[jxb] * ay[jyb]), w3 = make_float2(ax[jxa] * ay[jya], ax[jxb] * ay[jyb]);
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = fmaf(t11[k], w3, fmaf(t10[k], w2, fmaf(t01[k], w1, t00[k] * w0)));
+      for (int k = 0; k < SFE_SLOTS; ++k)
+        v[p][k] = fma2(both(t11[k]), w3, fma2(both(t10[k]), w2, fma2(both(t01[k]), w1, mul2(both(t00[k]), w0))));
     }
   } else {
 #pragma unroll
-    for (int s = 0; s < 6; ++s)
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
-      for (int k = 0; k < SFE_SLOTS; ++k) v[s][k] = S.v[(s * SFE_SLOTS + k) * 32 + lane];
+      for (int k = 0; k < SFE_SLOTS; ++k)
+        v[p][k] = make_float2(S.v[(2 * p * SFE_SLOTS + k) * 32 + lane], S.v[((2 * p + 1) * SFE_SLOTS + k) * 32 + lane]);
   }
 #pragma unroll
-  for (int s = 0; s < 6; ++s) {
-    float sm = 0.f, sq = 0.f;
+  for (int p = 0; p < 3; ++p) {
+    float2 sm = both(0.f), sq = both(0.f);
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
-      sm = sm + v[s][k];
-      sq = fmaf(v[s][k], v[s][k], sq);
+      sm = add2(sm, v[p][k]);
+      sq = fma2(v[p][k], v[p][k], sq);
     }
-    st[s] = sm;
-    st[8 + s] = sq;
+    st[2 * p] = sm.x;
+    st[2 * p + 1] = sm.y;
+    st[8 + 2 * p] = sq.x;
+    st[8 + 2 * p + 1] = sq.y;
   }
   st[6] = st[7] = st[14] = st[15] = 0.f;
   const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
@@ -346,17 +376,20 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     mkT[k] = S.mkT[k * 32 + lane];
   }
   if (!zeros) {
+    const float nalpha_l = -alpha_l, nbeta_l = -beta_l;  // (-v)*alpha == v*(-alpha) and x - beta == x + (-beta), exactly
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
-      float p = 0.f;
+    for (int p = 0; p < 3; ++p) {
+      const float2 na = make_float2(__shfl_sync(SFE_FULL, nalpha_l, 4 * p), __shfl_sync(SFE_FULL, nalpha_l, 4 * p + 2));
+      const float2 nb = make_float2(__shfl_sync(SFE_FULL, nbeta_l, 4 * p), __shfl_sync(SFE_FULL, nbeta_l, 4 * p + 2));
+      float2 acc = both(0.f);
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139; template zeros are folded into mkT
-        float diff = fmaf(-v[s][k], alpha, T[k]) - beta;
-        diff = diff * diff;
-        p = fmaf(diff, mkT[k], p);
+        float2 diff = add2(fma2(v[p][k], na, both(T[k])), nb);
+        diff = mul2(diff, diff);
+        acc = fma2(diff, both(mkT[k]), acc);
       }
-      part[s] = p;
+      part[2 * p] = acc.x;
+      part[2 * p + 1] = acc.y;
     }
   } else {
     // candidate pixels may be exactly 0 (hessian.h:134 skips them): rare, so a compact rolled loop over S.v
