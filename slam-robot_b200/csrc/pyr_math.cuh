@@ -30,6 +30,16 @@ __device__ __forceinline__ float blur_col(float m2, float m1, float c, float p1,
   return fmaf(t.k2, m2 + p2, r);
 }
 
+// packed forms (two neighbouring columns per instruction), operation for operation the scalar ones
+__device__ __forceinline__ float2 blur_col2(float2 m2, float2 m1, float2 c, float2 p1, float2 p2, Taps t) {
+  float2 r = mul2(c, both(t.k0));
+  r = fma2(both(t.k1), add2(m1, p1), r);
+  return fma2(both(t.k2), add2(m2, p2), r);
+}
+__device__ __forceinline__ float2 pd_v2(float2 r0, float2 r1, float2 r2, float2 r3, float2 r4) {
+  return mul2(add2(mul2(add2(add2(r1, r3), r2), both(4.f)), add2(add2(r0, r4), add2(r2, r2))), both(1.f / 256.f));
+}
+
 __device__ __forceinline__ float pd_h(float m2, float m1, float c, float p1, float p2) {
   return ((m2 + p2) + (m1 + p1) * 4.f) + c * 6.f;
 }

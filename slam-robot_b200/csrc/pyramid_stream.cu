@@ -43,7 +43,6 @@ struct StreamArgs {
   int w1, h1;              // size of the downsampled level: w/2, (h+1)/2
   int first;               // first frame slot in the pyramid batch
   int strips, bands, band_rows, nunits;
-  int blur0, blur1;        // tap sets of the two Gaussian blurs
 };
 
 __device__ __forceinline__ float gray_px(uint32_t p) {
@@ -86,7 +85,9 @@ __device__ __forceinline__ void issue_row(uint32_t slot_addr, const StreamArgs& 
 }
 
 // One warp = one (frame, row band, column strip) unit.
-template <bool FROM_BGR>
+// BLUR0 / BLUR1 select the Gaussian tap sets at compile time: as immediates the taps let FMUL/FFMA issue at the full
+// rate (the three-register forms issue every other cycle, and this kernel is FP-pipe bound).
+template <bool FROM_BGR, int BLUR0, int BLUR1>
 __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   const int lane = threadIdx.x;
   const int unit = blockIdx.x;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   const int r0 = band * a.band_rows;                           // band of input rows [r0, r1); band_rows is even
   const int r1 = min(r0 + a.band_rows, 2 * a.h1);
   const int q_hi = min(r1, a.h), j_lo = r0 >> 1, j_hi = min(r1 >> 1, a.h1);
-  const Taps k0 = taps_for(a.blur0), k1 = taps_for(a.blur1);
+  const Taps k0 = taps_for(BLUR0), k1 = taps_for(BLUR1);
 
   const uint8_t* bgr_px = nullptr;
   const float* in_px = nullptr;
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         hbw[u % 5] = hb;
         // GaussianBlur columns: level-0 row q = t-2 from rows t-4..t
         const float4 &h0 = hbw[(u + 1) % 5], &h1 = hbw[(u + 2) % 5], &h2 = hbw[(u + 3) % 5], &h3 = hbw[(u + 4) % 5], &h4 = hbw[u % 5];
-        row.x = blur_col(h0.x, h1.x, h2.x, h3.x, h4.x, k0);
-        row.y = blur_col(h0.y, h1.y, h2.y, h3.y, h4.y, k0);
-        row.z = blur_col(h0.z, h1.z, h2.z, h3.z, h4.z, k0);
-        row.w = blur_col(h0.w, h1.w, h2.w, h3.w, h4.w, k0);
+        const float2 rxy = blur_col2(make_float2(h0.x, h0.y), make_float2(h1.x, h1.y), make_float2(h2.x, h2.y),
+                                     make_float2(h3.x, h3.y), make_float2(h4.x, h4.y), k0);
+        const float2 rzw = blur_col2(make_float2(h0.z, h0.w), make_float2(h1.z, h1.w), make_float2(h2.z, h2.w),
+                                     make_float2(h3.z, h3.w), make_float2(h4.z, h4.w), k0);
+        row = make_float4(rxy.x, rxy.y, rzw.x, rzw.y);
         if (useful && q >= r0 && q < q_hi) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
       } else {
         row = *reinterpret_cast<const float4*>(&ring[u % RING][lane * LANE_BYTES]);
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
       if (u % 2 == 0) {
         // pyrDown columns: row i = (q-2)/2 from input rows q-4..q
         const float2 &p0 = phw[(u + 1) % 5], &p1 = phw[(u + 2) % 5], &p2 = phw[(u + 3) % 5], &p3 = phw[(u + 4) % 5], &p4 = phw[u % 5];
-        const float pa = pd_v(p0.x, p1.x, p2.x, p3.x, p4.x), pb = pd_v(p0.y, p1.y, p2.y, p3.y, p4.y);
+        const float2 pab = pd_v2(p0, p1, p2, p3, p4);
+        const float pa = pab.x, pb = pab.y;
         const int i = (q - 2) >> 1;
         // GaussianBlur rows on the pyrDown row: columns c0-2, c0-1 from the left lane, c0+2, c0+3 from the right lane
         float la = __shfl_up_sync(SFE_FULL, pa, 1), lb = __shfl_up_sync(SFE_FULL, pb, 1);
@@ -205,8 +208,7 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         const float2 &b0 = bhw[(v + 1) % 5], &b1 = bhw[(v + 2) % 5], &b2 = bhw[(v + 3) % 5], &b3 = bhw[(v + 4) % 5], &b4 = bhw[v];
         const int j = i - 2;
         if (useful && j >= j_lo && j < j_hi)
-          *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) =
-              make_float2(blur_col(b0.x, b1.x, b2.x, b3.x, b4.x, k1), blur_col(b0.y, b1.y, b2.y, b3.y, b4.y, k1));
+          *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) = blur_col2(b0, b1, b2, b3, b4, k1);
       }
     }
   }
@@ -221,7 +223,7 @@ int stream_slots() {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_stream_kernel<FROM_BGR>, 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_stream_kernel<FROM_BGR, 0, 1>, 32, 0);
     s = sms * (per_sm > 0 ? per_sm : 1);
   }
   return s;
@@ -264,17 +266,15 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
     a.first = first;
     a.strips = (a.w + STRIP_USEFUL - 1) / STRIP_USEFUL;
     a.out1 = v.base[0][l]; a.out1_fs = v.frame_stride[l]; a.out1_pitch = v.pitch[l];
-    a.blur1 = 1;  // sigma 0.8 (hessian.h:113)
     if (l == 1) {
       a.bgr = bgr; a.row_stride = row_stride; a.frame_stride = frame_stride;
       a.out0 = v.base[0][0]; a.out0_fs = v.frame_stride[0]; a.out0_pitch = v.pitch[0];
-      a.blur0 = 0;  // sigma 1.1 (hessian.h:102)
       plan_bands<true>(a, count);
-      pyr_stream_kernel<true><<<a.nunits, 32, 0, s>>>(a);
+      pyr_stream_kernel<true, 0, 1><<<a.nunits, 32, 0, s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
     } else {
       a.in = v.base[0][l - 1]; a.in_fs = v.frame_stride[l - 1]; a.in_pitch = v.pitch[l - 1];
       plan_bands<false>(a, count);
-      pyr_stream_kernel<false><<<a.nunits, 32, 0, s>>>(a);
+      pyr_stream_kernel<false, 0, 1><<<a.nunits, 32, 0, s>>>(a);
     }
     ++*launches;
     built = l + 1;

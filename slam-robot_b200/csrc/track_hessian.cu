@@ -172,31 +172,6 @@ __device__ __forceinline__ double div_h(double x) {
   return __fma_rn(r, y, q);
 }
 
-// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE single-precision operations per instruction, each rounded
-// exactly like its scalar form).  The kernel is bound by instruction issue, not by the FMA pipe, so the element-wise
-// work of the six candidate patches is done on PAIRS OF SHIFTS: .x = shift 2p, .y = shift 2p+1.  A scalar operand is
-// written {s, s}; ptxas turns that into the instruction's broadcast form, no move is issued.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 both(float s) { return make_float2(s, s); }
-
 // Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
 // returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
 __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
