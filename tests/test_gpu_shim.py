@@ -54,3 +54,37 @@ def test_cpp_shim_matches_oracle(tmp_path, po, synth, sfe):
         assert np.float32(float.fromhex(o[3])) == xy[0] and np.float32(float.fromhex(o[4])) == xy[1]
     b_line = [l for l in lines if l.startswith("after_B")][0].split()
     assert int(b_line[6]) == (0 if len(exp) >= 40 else 1)  # >= 40 matches: not a keyframe (matcher.cpp:353)
+
+
+def test_replay_dir_tool_matches_oracle(tmp_path, po, synth, sfe):
+    """The reference's --load replay format end to end on the GPU: PNG frames written with cv2 ("%08d.png", alternating
+    cameras -> pairs (id, id+2)) -> tools/replay_dir (PNG decode, sfe_good_features, sfe_replay_pairs) == the oracle."""
+    import cv2
+    sfe.build()
+    exe = str(tmp_path / "replay_dir")
+    csrc = os.path.join(ROOT, "slam-robot_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-o", exe, os.path.join(ROOT, "tools", "replay_dir.cpp"),
+                           "-L" + csrc, "-lslamfe", "-Wl,-rpath," + csrc])
+    H, W = 240, 320
+    d = tmp_path / "rec"
+    d.mkdir()
+    # two interleaved cameras: ids 0,2,4 are one moving view, ids 1,3 another
+    A, B = synth.make_pairs(51, 3, H, W)
+    frames = {0: A[0].numpy(), 2: B[0].numpy(), 4: B[2].numpy(), 1: A[1].numpy(), 3: B[1].numpy()}
+    for i, f in frames.items():
+        cv2.imwrite(str(d / ("%08d.png" % i)), f)
+    out = tmp_path / "tracks.txt"
+    r = subprocess.run([exe, str(d), "8", str(out)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("pair ")]
+    assert len(lines) == 3                                  # (0,2) (1,3) (2,4); (3,5) has no second frame
+    rows = [l.split() for l in open(out)]
+    for p, (a, b) in enumerate(((0, 2), (1, 3), (2, 4))):
+        corners = po.good_features(frames[a], 120, 0.01, 20.0)
+        oa, ob = po.Pyramid(frames[a], 6), po.Pyramid(frames[b], 6)
+        o = po.hes_track_fb(oa, ob, corners, corners, 3)
+        assert int(lines[p][3]) == len(corners) and int(lines[p][5]) == int(o["accepted"].sum()), (p, lines[p])
+        mine = [r_ for r_ in rows if int(r_[0]) == p]
+        assert len(mine) == len(corners)
+        got = np.float32([[float.fromhex(r_[4]), float.fromhex(r_[5])] for r_ in mine])
+        assert np.array_equal(got.view(np.uint32), o["to_xy"].view(np.uint32))

@@ -192,6 +192,48 @@ def test_seed_and_yuyv_oracles_against_independent_restatements(po):
     assert np.array_equal(po.yuyv_to_bgr(buf), px.ravel())
 
 
+def test_replay_source_reads_the_reference_png_format(tmp_path):
+    """SURVEY.md 8f rank 2: ImageSourceFiles (video.h:24-38) reads "<dir>/%08d.png" through cv::imread.  The C++ mirror
+    (host/replay_source.hpp, own PNG decoder) must return the bytes cv2.imread returns: colour frames at every zlib
+    level (stored / fixed / dynamic Huffman blocks, all five scanline filters), gray, RGBA and palette files; a missing
+    frame ends the sequence like main.cpp:518-519."""
+    import subprocess
+    import cv2
+    exe = str(tmp_path / "test_replay_source")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_replay_source.cpp")])
+    d = tmp_path / "frames"
+    d.mkdir()
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:60, 0:83]
+    smooth = np.stack([(xx * 3) % 256, (yy * 4) % 256, ((xx + yy) * 2) % 256], 2).astype(np.uint8)
+    frames = []
+    for i in range(7):
+        img = smooth.copy() if i % 2 else rng.integers(0, 256, (60, 83, 3), dtype=np.uint8)
+        img[10:20, 5:40] = 17 * i          # flat runs -> long matches
+        frames.append(img)
+    cv2.imwrite(str(d / "00000000.png"), frames[0], [cv2.IMWRITE_PNG_COMPRESSION, 0])       # stored blocks
+    cv2.imwrite(str(d / "00000001.png"), frames[1], [cv2.IMWRITE_PNG_COMPRESSION, 9])
+    cv2.imwrite(str(d / "00000002.png"), frames[2], [cv2.IMWRITE_PNG_COMPRESSION, 1, cv2.IMWRITE_PNG_STRATEGY, cv2.IMWRITE_PNG_STRATEGY_FIXED])
+    cv2.imwrite(str(d / "00000003.png"), frames[3][..., 0])                                # 8-bit gray
+    cv2.imwrite(str(d / "00000004.png"), np.dstack([frames[4], np.full((60, 83), 200, np.uint8)]))  # RGBA
+    cv2.imwrite(str(d / "00000005.png"), frames[5], [cv2.IMWRITE_PNG_COMPRESSION, 6, cv2.IMWRITE_PNG_STRATEGY, cv2.IMWRITE_PNG_STRATEGY_FILTERED])
+    cv2.imwrite(str(d / "00000006.png"), frames[6])
+    r = subprocess.run([exe, str(d), "0", "8", str(tmp_path / "out")], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    for i in range(8):
+        raw = open(tmp_path / ("out%d.bin" % i), "rb").read()
+        head, _, body = raw.partition(b"\n")
+        w, h = (int(v) for v in head.split())
+        ref = cv2.imread(str(d / ("%08d.png" % i)), cv2.IMREAD_COLOR)
+        if ref is None:
+            assert (w, h) == (0, 0) and i == 7
+            continue
+        assert (h, w) == ref.shape[:2], i
+        assert np.array_equal(np.frombuffer(body, np.uint8).reshape(h, w, 3), ref), "frame %d" % i
+    # frames 0..6 exist: pairs (0,2) (1,3) (2,4) (3,5) (4,6); (5,7) has no second frame
+    assert r.stdout.split()[:4] == ["pairs", "5", "83", "60"]
+
+
 def test_hamming_edge_cases(po):
     q = np.zeros((3, 8), np.uint32)
     idx, dist, ok = po.hamming256_top2(q, np.zeros((0, 8), np.uint32))
