@@ -164,8 +164,11 @@ def run_gpu(args):
     from_xy = torch.from_numpy(pts).to(dev)
     to_xy = torch.empty_like(from_xy)
     q_d, t_d = torch.from_numpy(q.view(np.int32)).to(dev), torch.from_numpy(t.view(np.int32)).to(dev)
-    pa = fe.pyramid(W, H, DEPTH, sfe.HESSIAN, B)
-    pb = fe.pyramid(W, H, DEPTH, sfe.HESSIAN, B)
+    # one pyramid batch of 2B slots: slots [0, B) hold the first frames of the pairs, [B, 2B) the second frames, so
+    # that all 2B pyramids of a step are built by ONE sfe_pyr_build_dev call (the frames sit in one device buffer)
+    frames = torch.cat([A, Bf]).contiguous()
+    del A, Bf
+    pyr = fe.pyramid(W, H, DEPTH, sfe.HESSIAN, 2 * B)
     trk_out = dict(back_xy=torch.empty_like(from_xy), status_fwd=torch.empty(n, dtype=torch.int32, device=dev),
                    status_bwd=torch.empty(n, dtype=torch.int32, device=dev), accepted=torch.empty(n, dtype=torch.uint8, device=dev),
                    steps=torch.empty(n, dtype=torch.int32, device=dev))
@@ -174,11 +177,11 @@ def run_gpu(args):
 
     def step(ev=None):
         if ev: ev[0].record(stream)
-        pa.build(A)
-        pb.build(Bf)
+        pyr.build(frames)
         if ev: ev[1].record(stream)
         to_xy.copy_(from_xy)  # seed = from_pt (the uncertainty >= 100 branch, matcher.cpp:225)
-        fe.track_fb(pa, pb, from_xy, to_xy, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=trk_out)
+        fe.track_fb(pyr, pyr, from_xy, to_xy, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, from_first=0, to_first=B,
+                    out=trk_out)
         if ev: ev[2].record(stream)
         fe.match_hamming256(q_d, t_d, *RATIO, batch=B, out=ham_out)
         if ev: ev[3].record(stream)
@@ -227,7 +230,7 @@ def run_gpu(args):
     # ---- end to end through the host-pointer C ABI (the call a user makes): pinned host inputs, results back
     # in host memory.  sfe_replay_pairs pipelines the step in chunks (upload | pyramids + tracking | download);
     # the descriptor matching of the step is enqueued first with sfe_match_hamming256_async and drains with it.
-    hA, hB = A.cpu().pin_memory(), Bf.cpu().pin_memory()
+    hA, hB = frames[:B].cpu().pin_memory(), frames[B:].cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
     fe.set_stream(None)
     h_pts = fe.pinned((n, 2), np.float32)
@@ -267,7 +270,7 @@ def run_gpu(args):
         peak, peak_src = peaks()
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
-        pyr_bytes = 2 * B * pa.bytes_per_frame()                      # per step, both pyramids of every pair
+        pyr_bytes = 2 * B * pyr.bytes_per_frame()                      # per step, both pyramids of every pair
         trk_bytes = pyr_bytes - 2 * B * 3 * W * H + n * 45            # read both pyramids once + 45 B/feature
         trk_ms = ms_trk / args.steps
         pyr_ms = ms_pyr / args.steps
@@ -297,7 +300,8 @@ def run_gpu(args):
                          "bilinear_samples_per_sec": newton * 6 * 169 / args.steps / 1.0 / (trk_ms * 1e-3) if False else
                          (newton * 6 * 169) / (trk_ms * 1e-3)},
             # the HBM-streaming kernels of the path
-            "roofline_pyramid": {"kernel": "pyr_stream_kernel<bgr> (levels 0+1 fused) + pyr_stream_kernel<down> x2", "bound": "hbm",
+            "roofline_pyramid": {"kernel": "pyr_row_kernel (levels 0+1 fused) + pyr_stream_kernel<down> x2, one build of 2B frames",
+                                 "bound": "hbm",
                                  "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": None,
                                  "share_of_step": pyr_ms / ms_step},
@@ -392,7 +396,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=512, help="frame pairs per step per GPU")
     ap.add_argument("--cpu-pairs", type=int, default=4, help="frame pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

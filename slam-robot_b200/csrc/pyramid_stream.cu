@@ -214,6 +214,206 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Row-CTA variant of the fused level-0 + level-1 kernel, for widths of NW * 128 columns.
+//
+// The strip kernel above spends 4 of its 32 lanes per warp on halo columns and (at 640 columns) rounds 5.7 strips
+// up to 6: 768 lane-columns work for 640 image columns.  Here a CTA owns the FULL width of a row band -- warp k
+// the columns [128k, 128k+128), no halo lanes -- and the neighbour pixels of the three horizontal filters travel
+// through row buffers in shared memory instead of warp shuffles, which cannot cross a warp boundary.  To pay one
+// barrier per tick instead of one per horizontal stage, every horizontal stage consumes the row its producer
+// published ONE TICK EARLIER (the own-lane values simply stay in registers for a tick): a tick is
+//     barrier; all stages, each reading last tick's row buffers and writing this tick's (double-buffered).
+// The lag also makes the stages of one tick independent of each other -- instruction-level parallelism the strip
+// kernel's dependent chain does not have.  Image borders (BORDER_REFLECT_101) cost no selects: the row buffers
+// have one extra slot on each side, which the first / last lane of the row fill with their own mirrored pixels.
+// Per-pixel arithmetic and operation order are unchanged (pyr_math.cuh): bit-identical to the strip kernel.
+
+// gray value of one pixel from the doubled-coefficient dot product (the gray byte sits in bits 16..23):
+// 0x4b0000XX is the float 8388608 + XX, and fma(8388608 + v, c, -8388608 c) rounds the exact product v*c once,
+// i.e. it equals (float)v * c bit for bit (hessian.h:100-101) without the shift and the integer conversion.
+__device__ __forceinline__ float gray_from_dot(unsigned s2) {
+  const float c = (float)(1. / 255.);
+  return fmaf(__uint_as_float(__byte_perm(s2, 0x4b000000u, 0x7652)), c, -8388608.f * c);
+}
+
+// the four pixels of 12 BGR bytes; the 16-bit coefficient pairs are placed so that no byte has to be shifted
+__device__ __forceinline__ float4 gray4(uint32_t ra, uint32_t rb, uint32_t rc) {
+  constexpr unsigned C0 = 2 * 9798u, C1 = 2 * 19235u, C2 = 2 * 3735u, RND = 1u << 15;
+  float4 g;
+  g.x = gray_from_dot(__dp2a_hi(C2, ra, __dp2a_lo(C0 | (C1 << 16), ra, RND)));          // ra.b0 ra.b1 ra.b2
+  g.y = gray_from_dot(__dp2a_lo(C1 | (C2 << 16), rb, __dp2a_hi(C0 << 16, ra, RND)));    // ra.b3 rb.b0 rb.b1
+  g.z = gray_from_dot(__dp2a_lo(C2, rc, __dp2a_hi(C0 | (C1 << 16), rb, RND)));          // rb.b2 rb.b3 rc.b0
+  g.w = gray_from_dot(__dp2a_hi(C1 | (C2 << 16), rc, __dp2a_lo(C0 << 16, rc, RND)));    // rc.b1 rc.b2 rc.b3
+  return g;
+}
+
+// Shared-memory accesses of the row buffers as PTX: addresses are 32-bit shared-window offsets plus immediates,
+// and the border stores stay single predicated instructions (as C++ `if (lane == 0) ...` they become divergent
+// branches, which cost more than the selects they replace).
+__device__ __forceinline__ void sts2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" :: "r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts1_if(int p, uint32_t addr, float a) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.shared.f32 [%1], %2;\n\t}"
+               :: "r"(p), "r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float2 lds2(uint32_t addr) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+  return r;
+}
+
+// Row buffers of one CTA (NL = 32 NW lanes, lane L holds columns 4L..4L+3 resp. level-1 columns 2L, 2L+1).
+// A row is split into an xy plane and a zw plane so that every access is a conflict-free 8-byte stride:
+//   xy[L] = columns 4L, 4L+1 (L = 0..NL; slot NL = the two columns right of the image)
+//   zw[L+1] = columns 4L+2, 4L+3 (slot 0 = the two columns left of the image)
+template <int NW>
+struct RowBufs {
+  static constexpr int NL = 32 * NW;
+  float2 gxy[2][NL + 1], gzw[2][NL + 1];   // gray rows (double-buffered: written in tick t, read in tick t+1)
+  float2 lxy[2][NL + 1], lzw[2][NL + 1];   // level-0 rows
+  float2 pd[NL + 2];                       // pyrDown row: pd[L+1]; written in even ticks, read in odd ticks
+};
+
+template <int NW, int BLUR0, int BLUR1>
+#ifndef ROW_MINB5
+#define ROW_MINB5 4  // measured: 4 CTAs x 5 warps at 94 registers beat 5 CTAs at 72 (profiles/README.md)
+#endif
+__global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 : 1)) pyr_row_kernel(const StreamArgs a) {
+  using Bufs = RowBufs<NW>;
+  extern __shared__ __align__(16) unsigned char row_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, L = threadIdx.x;
+  const int band = blockIdx.x % a.bands;
+  const int frame = blockIdx.x / a.bands;
+  unsigned char* ring = row_smem + sizeof(Bufs) + (size_t)warp * RING * 32 * 12;
+
+  const int g = 4 * L;
+  const int r0 = band * a.band_rows;
+  const int r1 = min(r0 + a.band_rows, 2 * a.h1);
+  const int q_hi = min(r1, a.h), j_lo = r0 >> 1, j_hi = min(r1 >> 1, a.h1);
+  const Taps k0 = taps_for(BLUR0), k1 = taps_for(BLUR1);
+
+  const uint8_t* bgr_px = a.bgr + (size_t)frame * a.frame_stride + 3 * (size_t)g;
+  float* out0_px = a.out0 + (long long)(a.first + frame) * a.out0_fs + g;
+  float* out1_px = a.out1 + (long long)(a.first + frame) * a.out1_fs + (g >> 1);
+
+  // every buffer access of this lane is `lb` plus a compile-time offset
+  const uint32_t lb = (uint32_t)__cvta_generic_to_shared(row_smem) + 8 * L;
+  constexpr uint32_t GXY = offsetof(Bufs, gxy), GZW = offsetof(Bufs, gzw), LXY = offsetof(Bufs, lxy), LZW = offsetof(Bufs, lzw),
+                     PD = offsetof(Bufs, pd), BUF = 8 * (Bufs::NL + 1);
+  // image borders: the first lane of the row also fills zw slot 0 (columns -2, -1 = 2, 1), the last lane xy slot NL
+  // (columns w, w+1 = w-2, w-3); both are (z, y) of the lane.  `mb` is that slot relative to GXY + buffer offset.
+  const int mirror = L == 0 || L == Bufs::NL - 1;
+  const uint32_t mb = L == 0 ? lb + (GZW - GXY) : lb + 8;
+  // pyrDown row: slot 0 = columns (2, 1) = (pa of lane 1, pb of lane 0); slot NL+1 = columns (w1-2, w1-3) =
+  // (pa of the last lane, pb of the one before): odd lanes store their pa into .x, even lanes their pb into .y
+  const int pd_mirror = L < 2 || L >= Bufs::NL - 2;
+  const uint32_t pmb = (L < 2 ? lb - 8 * L : lb + 8 * (Bufs::NL + 1 - L)) + PD + ((L & 1) ? 0 : 4);
+
+  // Tick t: BGR row t arrives and becomes gray(t); the lagged stages then work on
+  //   gray(t-1) -> horizontally blurred row t-1 -> level-0 row q = t-3
+  //   level-0 row qd = t-4 -> horizontally pyrDown-filtered row qd -> (qd even) pyrDown row i = (qd-2)/2
+  //   (qd odd) the pyrDown row i = (qd-3)/2 of the previous tick -> blurred rows -> level-1 row j = i-2.
+  const int t_begin = r0 - 8;   // even: qd is even exactly when the unrolled tick index is
+  const int t_last = r1 + 9;
+  const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring + lane * 12);
+#pragma unroll
+  for (int u = 0; u < PREFETCH; ++u) issue_row<true>(ring_addr + u * 32 * 12, a, bgr_px, nullptr, t_begin + u, 4);
+
+  float4 hbw[5];   // horizontally blurred gray rows t-5..t-1
+  float2 phw[5];   // horizontally pyrDown-filtered rows qd-4..qd
+  float2 bhw[5];   // horizontally blurred pyrDown rows i-4..i
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    hbw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    phw[u] = bhw[u] = make_float2(0.f, 0.f);
+  }
+  float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);     // gray(t-1)
+  float4 rowp = make_float4(0.f, 0.f, 0.f, 0.f);   // level-0 row t-4
+  float2 pdp = make_float2(0.f, 0.f);              // pyrDown row formed in the previous (even) tick
+
+#pragma unroll 1
+  for (int tb = t_begin; tb <= t_last; tb += 10) {
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int t = tb + u;
+      const uint32_t cur = (u & 1) * BUF, prev = ((u + 1) & 1) * BUF;
+      __syncthreads();
+      asm volatile("cp.async.wait_group %0;" ::"n"(PREFETCH - 1) : "memory");
+      issue_row<true>(ring_addr + ((u + PREFETCH) % RING) * 32 * 12, a, bgr_px, nullptr, t + PREFETCH, 4);
+
+      // ---- gray(t), published for the next tick
+      const uint32_t* rr = reinterpret_cast<const uint32_t*>(ring + ((u % RING) * 32 + lane) * 12);
+      const float4 gn = gray4(rr[0], rr[1], rr[2]);
+      sts2(lb + GXY + cur, gn.x, gn.y);
+      sts2(lb + GZW + cur + 8, gn.z, gn.w);
+      sts1_if(mirror, mb + GXY + cur, gn.z);
+      sts1_if(mirror, mb + GXY + cur + 4, gn.y);
+
+      // ---- GaussianBlur rows on gray(t-1): columns g-2, g-1 and g+4, g+5 from last tick's buffer
+      {
+        const float2 l = lds2(lb + GZW + prev), r = lds2(lb + GXY + prev + 8);
+        float4 hb;
+        hb.x = blur_row(l.x, l.y, gp.x, gp.y, gp.z, k0);
+        hb.y = blur_row(l.y, gp.x, gp.y, gp.z, gp.w, k0);
+        hb.z = blur_row(gp.x, gp.y, gp.z, gp.w, r.x, k0);
+        hb.w = blur_row(gp.y, gp.z, gp.w, r.x, r.y, k0);
+        hbw[(u + 4) % 5] = hb;
+      }
+      // ---- GaussianBlur columns: level-0 row q = t-3 from rows t-5..t-1; stored, and published for the next tick
+      const int q = t - 3;
+      const float4 &h0 = hbw[u % 5], &h1 = hbw[(u + 1) % 5], &h2 = hbw[(u + 2) % 5], &h3 = hbw[(u + 3) % 5], &h4 = hbw[(u + 4) % 5];
+      const float2 rxy = blur_col2(make_float2(h0.x, h0.y), make_float2(h1.x, h1.y), make_float2(h2.x, h2.y),
+                                   make_float2(h3.x, h3.y), make_float2(h4.x, h4.y), k0);
+      const float2 rzw = blur_col2(make_float2(h0.z, h0.w), make_float2(h1.z, h1.w), make_float2(h2.z, h2.w),
+                                   make_float2(h3.z, h3.w), make_float2(h4.z, h4.w), k0);
+      const float4 row = make_float4(rxy.x, rxy.y, rzw.x, rzw.y);
+      if (q >= r0 && q < q_hi) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
+      sts2(lb + LXY + cur, row.x, row.y);
+      sts2(lb + LZW + cur + 8, row.z, row.w);
+      sts1_if(mirror, mb + LXY + cur, row.z);
+      sts1_if(mirror, mb + LXY + cur + 4, row.y);
+
+      // ---- pyrDown rows on level-0 row qd = t-4: columns g-2, g-1 and g+4 from last tick's buffer
+      {
+        const float2 l = lds2(lb + LZW + prev);
+        const float r = lds1(lb + LXY + prev + 8);
+        phw[u % 5] = make_float2(pd_h(l.x, l.y, rowp.x, rowp.y, rowp.z), pd_h(rowp.x, rowp.y, rowp.z, rowp.w, r));
+      }
+      if (u % 2 == 0) {
+        // pyrDown columns: row i = (qd-2)/2 from level-0 rows qd-4..qd, published for the next tick
+        const float2 &p0 = phw[(u + 1) % 5], &p1 = phw[(u + 2) % 5], &p2 = phw[(u + 3) % 5], &p3 = phw[(u + 4) % 5], &p4 = phw[u % 5];
+        pdp = pd_v2(p0, p1, p2, p3, p4);
+        sts2(lb + PD + 8, pdp.x, pdp.y);
+        sts1_if(pd_mirror, pmb, (L & 1) ? pdp.x : pdp.y);
+      } else {
+        // GaussianBlur rows on the pyrDown row of the previous tick: columns c0-2, c0-1 and c0+2, c0+3
+        const int i = (t - 7) >> 1;
+        const float2 l = lds2(lb + PD), r = lds2(lb + PD + 16);
+        float2 bh = make_float2(blur_row(l.x, l.y, pdp.x, pdp.y, r.x, k1), blur_row(l.y, pdp.x, pdp.y, r.x, r.y, k1));
+        const int v = (u / 2) % 5;
+        // below the image the pyrDown rows mirror about row h1-1: row h1 is row h1-2, row h1+1 is row h1-3
+        if (i == a.h1) bh = bhw[(v + 3) % 5];
+        if (i == a.h1 + 1) bh = bhw[(v + 1) % 5];
+        bhw[v] = bh;
+        const float2 &b0 = bhw[(v + 1) % 5], &b1 = bhw[(v + 2) % 5], &b2 = bhw[(v + 3) % 5], &b3 = bhw[(v + 4) % 5], &b4 = bhw[v];
+        const int j = i - 2;
+        if (j >= j_lo && j < j_hi)
+          *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) = blur_col2(b0, b1, b2, b3, b4, k1);
+      }
+      gp = gn;
+      rowp = row;
+    }
+  }
+}
+
 int g_slots[2] = {0, 0};  // resident warps of the two instantiations on this device (one warp per CTA)
 
 template <bool FROM_BGR>
@@ -249,6 +449,41 @@ void plan_bands(StreamArgs& a, int count) {
   a.nunits = count * a.strips * a.bands;
 }
 
+template <int NW>
+size_t row_smem_bytes() { return sizeof(RowBufs<NW>) + (size_t)NW * RING * 32 * 12; }
+
+// Bands of the row-CTA kernel: a CTA is NW warps, a band repeats 18 rows of pipeline fill.  All CTAs take the same
+// time, so what matters is how the grid quantises into waves: measured on B200 (128..1024 VGA frames, 1..8 bands,
+// profiles/README.md) the best grids hold about 1.73x the resident CTA slots -- one full wave plus a second one
+// that finishes quickly because its CTAs have the SMs almost to themselves -- or 0.86x when that is all there is.
+template <int NW>
+void launch_row(StreamArgs& a, int count, cudaStream_t s) {
+  static int slots = 0;  // resident CTAs on the device
+  if (slots == 0) {
+    int dev = 0, per_sm = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1>, 32 * NW, row_smem_bytes<NW>());
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int rows = 2 * a.h1;
+  static const double fill = getenv("SFE_PYR_ROW_FILL") ? atof(getenv("SFE_PYR_ROW_FILL")) : 1.73;  // experiments
+  int bands = (int)(fill * slots / (double)count + 0.5);
+  static const int forced = getenv("SFE_PYR_BANDS") ? atoi(getenv("SFE_PYR_BANDS")) : 0;
+  if (forced > 0) bands = forced;
+  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
+  if (bands < 1) bands = 1;
+  if (bands > max_bands) bands = max_bands;
+  int br = (rows + bands - 1) / bands;
+  br += br & 1;
+  a.band_rows = br;
+  a.bands = (rows + br - 1) / br;
+  a.strips = 1;
+  a.nunits = count * a.bands;
+  pyr_row_kernel<NW, 0, 1><<<a.nunits, 32 * NW, row_smem_bytes<NW>(), s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+}
+
 }  // namespace
 
 // Streams levels 0 and 1 of `count` frames (SFE_HESSIAN flavour) and then every deeper level the down
@@ -269,8 +504,14 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
     if (l == 1) {
       a.bgr = bgr; a.row_stride = row_stride; a.frame_stride = frame_stride;
       a.out0 = v.base[0][0]; a.out0_fs = v.frame_stride[0]; a.out0_pitch = v.pitch[0];
-      plan_bands<true>(a, count);
-      pyr_stream_kernel<true, 0, 1><<<a.nunits, 32, 0, s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+      static const bool strips_only = getenv("SFE_PYR_STRIPS") != nullptr;  // experiments: force the strip kernel
+      // row-CTA kernel for the widths it was tuned for; 1920 columns would be one 15-warp CTA per SM (slower than strips)
+      if (!strips_only && a.w == 640) launch_row<5>(a, count, s);
+      else if (!strips_only && a.w == 1280) launch_row<10>(a, count, s);
+      else {
+        plan_bands<true>(a, count);
+        pyr_stream_kernel<true, 0, 1><<<a.nunits, 32, 0, s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+      }
     } else {
       a.in = v.base[0][l - 1]; a.in_fs = v.frame_stride[l - 1]; a.in_pitch = v.pitch[l - 1];
       plan_bands<false>(a, count);

@@ -43,6 +43,37 @@ def test_pyramid_1080p_8_levels_bit_exact(fe, po, synth):
         assert_bits_equal(gp.plane(l), op.plane(l), "1080p level %d" % l)
 
 
+@pytest.mark.parametrize("shape,depth,nframes", [((480, 640), 4, 3), ((481, 640), 5, 2), ((97, 640), 3, 2), ((720, 1280), 6, 2),
+                                                 ((45, 1280), 2, 1), ((1080, 1920), 4, 1)])
+def test_pyramid_row_kernel_bit_exact(fe, po, synth, shape, depth, nframes):
+    """Widths of 640 / 1280 / 1920 columns take the row-CTA kernel (pyramid_stream.cu: one CTA per row band, neighbours
+    through shared row buffers, lagged stages): odd heights, bands shorter than the pipeline fill, several bands."""
+    H, W = shape
+    frames = synth.make_frames(11, nframes, H, W).numpy()
+    gp = fe.make_pyramid(frames, depth, 0)
+    for f in range(nframes):
+        op = po.Pyramid(frames[f], depth, 0)
+        for l in range(depth):
+            assert_bits_equal(gp.plane(l, f), op.plane(l), "%dx%d frame %d level %d" % (W, H, f, l))
+
+
+def test_pyramid_large_batch_single_band_bit_exact(fe, po, synth):
+    """A batch large enough that every frame is ONE row band (the band heuristic only cuts frames when the batch alone
+    cannot fill the GPU): first, middle and last frame of 1024 against the oracle."""
+    import torch
+    H, W, n = 480, 640, 1024
+    base = synth.make_frames(5, 32, H, W, device="cuda")
+    frames = base.repeat(n // 32, 1, 1, 1).contiguous()
+    frames[n // 2] = torch.flip(base[3], dims=[0])
+    frames[n - 1] = torch.flip(base[5], dims=[1])
+    gp = fe.pyramid(W, H, 4, 0, n)
+    gp.build(frames)
+    for f in (0, n // 2, n - 1):
+        op = po.Pyramid(frames[f].cpu().numpy(), 4, 0)
+        for l in range(4):
+            assert_bits_equal(gp.plane(l, f), op.plane(l), "frame %d level %d" % (f, l))
+
+
 def _features(synth, n, H, W, seed=5, border=0.2):
     return synth.make_features(seed, n, H, W, margin=16, border_frac=border)
 
