@@ -246,6 +246,7 @@ def run_gpu(args):
         fe.match_hamming256_async(h_q, h_t, h_ham, *RATIO, batch=B)
         r = fe.replay_pairs(hA, hB, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk,
                             chunk_pairs=int(os.environ.get("SFE_BENCH_CHUNK", "0")))
+        fe.sync()  # joins the matcher's side stream: every result of the step is in host memory when the step ends
         return r, h_ham
 
     step_e2e()

@@ -185,10 +185,12 @@ int sfe_match_hamming256_dev(sfe_ctx* ctx, const uint32_t* q, int nq, const uint
                              int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
                              int32_t* dist, uint8_t* pass);
 
-/* As sfe_match_hamming256, but only ENQUEUES the uploads, the kernels and the downloads on the
- * context's stream: the result buffers are valid after sfe_sync().  The host buffers must stay
- * alive until then (pinned memory from sfe_host_alloc makes the copies truly asynchronous); one
- * asynchronous call may be outstanding per context. */
+/* As sfe_match_hamming256, but only ENQUEUES the uploads, the kernels and the downloads: the
+ * result buffers are valid after sfe_sync().  The work is ordered after everything enqueued on
+ * the context's stream before the call, but runs on a side stream of the context, so that it
+ * overlaps with whatever is enqueued next (e.g. sfe_replay_pairs); only sfe_sync() joins it.
+ * The host buffers must stay alive until then (pinned memory from sfe_host_alloc makes the
+ * copies truly asynchronous); one asynchronous call may be outstanding per context. */
 int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt,
                                int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
                                int32_t* dist, uint8_t* pass);

@@ -180,6 +180,12 @@ void sfe_destroy(sfe_ctx* ctx) {
   sfe_replay_release(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
+  if (ctx->ham_stream) {
+    cudaStreamSynchronize(ctx->ham_stream);
+    cudaStreamDestroy(ctx->ham_stream);
+    cudaEventDestroy(ctx->ham_fork);
+    cudaEventDestroy(ctx->ham_done);
+  }
   if (ctx->ham_io) cudaFree(ctx->ham_io);
   if (ctx->gftt_ws) cudaFree(ctx->gftt_ws);
   cudaFree(ctx->d_mask);
@@ -199,6 +205,10 @@ int sfe_set_stream(sfe_ctx* ctx, void* cuda_stream) {
 int sfe_sync(sfe_ctx* ctx) {
   if (!ctx) return SFE_ERR_INVALID;
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ham_pending) {
+    CU(cudaStreamSynchronize(ctx->ham_stream));
+    ctx->ham_pending = false;
+  }
   return SFE_SUCCESS;
 }
 
@@ -552,6 +562,8 @@ int sfe_match_hamming256_dev(sfe_ctx* ctx, const uint32_t* q, int nq, const uint
   if (nt > (1 << 22)) return fail(ctx, SFE_ERR_INVALID, "%s", "nt exceeds 4M train descriptors per call");
   if (nq == 0) return SFE_SUCCESS;
   if (use_device(ctx)) return SFE_ERR_CUDA;
+  // the workspace is shared with an asynchronous match that may still be running on the side stream
+  if (ctx->ham_pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->ham_done, 0));
   return launched(ctx,
                   launch_hamming256(q, nq, t, nt, batch, ratio_num, ratio_den, max_dist, idx, dist, pass, &ctx->ham_ws,
                                     &ctx->ham_cap, ctx->stream),
@@ -590,12 +602,13 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
                                int ratio_num, int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass) {
   if (!ctx || nq < 0 || nt < 0 || batch < 1 || !idx || !dist || (nq && !q) || (nt && !t))
     return fail(ctx, SFE_ERR_INVALID, "%s", "bad hamming arguments");
+  if (nt > (1 << 22)) return fail(ctx, SFE_ERR_INVALID, "%s", "nt exceeds 4M train descriptors per call");
   if (nq == 0) return SFE_SUCCESS;
   if (use_device(ctx)) return SFE_ERR_CUDA;
   const size_t qb = 32 * (size_t)nq * batch, tb = 32 * (size_t)nt * batch, ob = 8 * (size_t)nq * batch;
   const size_t need = padded(qb) + padded(tb) + 2 * padded(ob) + padded((size_t)nq * batch);
   if (need > ctx->ham_io_cap) {
-    CU(cudaStreamSynchronize(ctx->stream));  // a previous asynchronous call may still be using the old buffers
+    if (ctx->ham_stream) CU(cudaStreamSynchronize(ctx->ham_stream));  // a previous asynchronous call may still be using the old buffers
     if (ctx->ham_io) CU(cudaFree(ctx->ham_io));
     ctx->ham_io = nullptr;
     ctx->ham_io_cap = 0;
@@ -609,14 +622,28 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
   int32_t* d_i = c.take<int32_t>(2 * (size_t)nq * batch);
   int32_t* d_d = c.take<int32_t>(2 * (size_t)nq * batch);
   uint8_t* d_p = c.take<uint8_t>((size_t)nq * batch);
-  cudaStream_t s = ctx->stream;
+  if (!ctx->ham_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->ham_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ham_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ham_done, cudaEventDisableTiming));
+  }
+  // fork: the match is ordered after everything enqueued on the context's stream so far, but nothing enqueued
+  // later waits for it; sfe_sync() joins
+  cudaStream_t s = ctx->ham_stream;
+  CU(cudaEventRecord(ctx->ham_fork, ctx->stream));
+  CU(cudaStreamWaitEvent(s, ctx->ham_fork, 0));
   CU(cudaMemcpyAsync(d_q, q, qb, cudaMemcpyHostToDevice, s));
   if (nt) CU(cudaMemcpyAsync(d_t, t, tb, cudaMemcpyHostToDevice, s));
-  int rc = sfe_match_hamming256_dev(ctx, d_q, nq, d_t, nt, batch, ratio_num, ratio_den, max_dist, d_i, d_d, pass ? d_p : nullptr);
+  int rc = launched(ctx,
+                    launch_hamming256(d_q, nq, d_t, nt, batch, ratio_num, ratio_den, max_dist, d_i, d_d, pass ? d_p : nullptr,
+                                      &ctx->ham_ws, &ctx->ham_cap, s),
+                    "hamming launch: %s");
   if (rc) return rc;
   CU(cudaMemcpyAsync(idx, d_i, ob, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(dist, d_d, ob, cudaMemcpyDeviceToHost, s));
   if (pass) CU(cudaMemcpyAsync(pass, d_p, (size_t)nq * batch, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(ctx->ham_done, s));
+  ctx->ham_pending = true;
   return SFE_SUCCESS;
 }
 

@@ -19,6 +19,11 @@ struct sfe_ctx {
   size_t ham_cap;
   void* ham_io;   // device buffers of sfe_match_hamming256_async (must outlive the call, so not the shared scratch)
   size_t ham_io_cap;
+  // sfe_match_hamming256_async runs on a side stream (forked from / joined into the context's stream by events), so
+  // that its uploads and kernels overlap with whatever the caller enqueues next, e.g. the sfe_replay_pairs pipeline
+  cudaStream_t ham_stream;
+  cudaEvent_t ham_fork, ham_done;
+  bool ham_pending;
   int64_t launches;
   sfe_replay* replay;  // lazily created by sfe_replay_pairs
   void* gftt_ws;   // corner-seeding workspace: response maps, maxima, candidate keys

@@ -1,10 +1,15 @@
 // replay.cu -- sfe_replay_pairs: the host-side batching/stream layer for replaying independent frame
 // pairs (BASELINE config 4; the per-frame body is matcher.cpp:317 MakePyramid + :208-271 FindMatches).
 //
-// Host buffers in, host buffers out.  The pairs are cut into chunks; three CUDA streams form a pipeline
-//   copy stream     H2D of the BGR frames of chunk k+1 (double-buffered device staging)
-//   compute streams MakePyramid of both frames + forward/backward tracking of chunk k; chunks alternate between
-//                   two streams so that the next chunk's kernels fill the SMs the persistent tracker's tail frees
+// Host buffers in, host buffers out.  The pairs are cut into chunks; CUDA streams form a pipeline
+//   copy stream     H2D of the BGR frames of chunk k+2 (double-buffered device staging)
+//   pyramid stream  MakePyramid of both frames of chunk k+1, HIGH priority and one of three pyramid sets: the
+//                   tracker is a persistent kernel that holds every SM until its queue is empty, so the pyramids of
+//                   the next chunk can only run in the gap between two trackers -- with the priority they take the
+//                   first SMs tracker k-1 frees, ahead of the CTAs of tracker k (whose pyramids were built one gap
+//                   earlier), and no tracker ever waits for its pyramids
+//   compute streams forward/backward tracking of chunk k; chunks alternate between two streams so that the next
+//                   tracker fills the SMs the previous one's tail frees
 //   output stream   D2H of the results of chunk k-1
 // ordered by events only, so with pinned host buffers (sfe_host_alloc) the PCIe traffic of a step hides
 // behind its kernels.  Staging buffers, pyramids and events are cached in the context between calls.
@@ -15,12 +20,11 @@
 #include "ctx.cuh"
 
 struct sfe_replay {
-  cudaStream_t copy_stream, out_stream, compute2;  // compute alternates between the context's stream and compute2
-  cudaEvent_t copied[2], consumed[2], tracked[2], drained;
+  cudaStream_t copy_stream, out_stream, compute2, pyr_stream;  // tracking alternates between the context's stream and compute2
+  cudaEvent_t copied[2], consumed[2], built[3], tracked[3], drained;
   int w, h, depth, chunk;  // geometry the frame buffers / pyramids were built for
-  uint8_t* d_frames[2];    // per buffer: `chunk` from-frames followed by `chunk` to-frames
-  sfe_pyr* pyr_from[2];
-  sfe_pyr* pyr_to[2];
+  uint8_t* d_frames[2];    // per buffer: the c from-frames of a chunk followed by its c to-frames (c <= chunk)
+  sfe_pyr* pyr[3];         // pyramid sets of 2 * chunk slots (from-frames, then to-frames): chunk k uses set k % 3
   size_t n_cap;            // feature capacity of the arrays below
   float *d_from, *d_to, *d_back;
   int32_t *d_lv, *d_s1, *d_s2, *d_steps;
@@ -42,12 +46,11 @@ int rfail(sfe_ctx* c, int code, const char* what, cudaError_t e) {
   } while (0)
 
 void free_geometry(sfe_replay* r) {
-  for (int b = 0; b < 2; ++b) {
-    if (r->d_frames[b]) cudaFree(r->d_frames[b]);
-    if (r->pyr_from[b]) sfe_pyr_destroy(r->pyr_from[b]);
-    if (r->pyr_to[b]) sfe_pyr_destroy(r->pyr_to[b]);
-    r->d_frames[b] = nullptr;
-    r->pyr_from[b] = r->pyr_to[b] = nullptr;
+  for (int b = 0; b < 3; ++b) {
+    if (b < 2 && r->d_frames[b]) cudaFree(r->d_frames[b]);
+    if (r->pyr[b]) sfe_pyr_destroy(r->pyr[b]);
+    if (b < 2) r->d_frames[b] = nullptr;
+    r->pyr[b] = nullptr;
   }
   r->w = r->h = r->depth = r->chunk = 0;
 }
@@ -72,9 +75,13 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
     RCU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
     RCU(cudaStreamCreateWithFlags(&r->out_stream, cudaStreamNonBlocking));
     RCU(cudaStreamCreateWithFlags(&r->compute2, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-      RCU(cudaEventCreateWithFlags(&r->copied[b], cudaEventDisableTiming));
-      RCU(cudaEventCreateWithFlags(&r->consumed[b], cudaEventDisableTiming));
+    int prio_least = 0, prio_greatest = 0;
+    RCU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    RCU(cudaStreamCreateWithPriority(&r->pyr_stream, cudaStreamNonBlocking, prio_greatest));
+    for (int b = 0; b < 3; ++b) {
+      if (b < 2) RCU(cudaEventCreateWithFlags(&r->copied[b], cudaEventDisableTiming));
+      if (b < 2) RCU(cudaEventCreateWithFlags(&r->consumed[b], cudaEventDisableTiming));
+      RCU(cudaEventCreateWithFlags(&r->built[b], cudaEventDisableTiming));
       RCU(cudaEventCreateWithFlags(&r->tracked[b], cudaEventDisableTiming));
     }
     RCU(cudaEventCreateWithFlags(&r->drained, cudaEventDisableTiming));
@@ -82,11 +89,10 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
   if (r->w != w || r->h != h || r->depth != depth || r->chunk != chunk) {
     RCU(cudaStreamSynchronize(ctx->stream));
     free_geometry(r);
-    for (int b = 0; b < 2; ++b) {
-      cudaError_t e = cudaMalloc(&r->d_frames[b], (size_t)2 * chunk * 3 * w * h);
+    for (int b = 0; b < 3; ++b) {
+      cudaError_t e = b < 2 ? cudaMalloc(&r->d_frames[b], (size_t)2 * chunk * 3 * w * h) : cudaSuccess;
       if (e != cudaSuccess) return rfail(ctx, SFE_ERR_NOMEM, "cudaMalloc(frame staging)", e);
-      int rc = sfe_pyr_create(ctx, w, h, depth, SFE_HESSIAN, chunk, &r->pyr_from[b]);
-      if (!rc) rc = sfe_pyr_create(ctx, w, h, depth, SFE_HESSIAN, chunk, &r->pyr_to[b]);
+      int rc = sfe_pyr_create(ctx, w, h, depth, SFE_HESSIAN, 2 * chunk, &r->pyr[b]);
       if (rc) return rc;
     }
     r->w = w; r->h = h; r->depth = depth; r->chunk = chunk;
@@ -130,15 +136,17 @@ void sfe_replay_release(sfe_ctx* ctx) {
   if (!r) return;
   free_geometry(r);
   free_features(r);
-  for (int b = 0; b < 2; ++b) {
-    if (r->copied[b]) cudaEventDestroy(r->copied[b]);
-    if (r->consumed[b]) cudaEventDestroy(r->consumed[b]);
+  for (int b = 0; b < 3; ++b) {
+    if (b < 2 && r->copied[b]) cudaEventDestroy(r->copied[b]);
+    if (b < 2 && r->consumed[b]) cudaEventDestroy(r->consumed[b]);
+    if (r->built[b]) cudaEventDestroy(r->built[b]);
     if (r->tracked[b]) cudaEventDestroy(r->tracked[b]);
   }
   if (r->drained) cudaEventDestroy(r->drained);
   if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   if (r->out_stream) cudaStreamDestroy(r->out_stream);
   if (r->compute2) cudaStreamDestroy(r->compute2);
+  if (r->pyr_stream) cudaStreamDestroy(r->pyr_stream);
   delete r;
   ctx->replay = nullptr;
 }
@@ -164,7 +172,7 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
   int rc = ensure(ctx, w, h, depth, chunk, n);
   if (rc) return rc;
   sfe_replay* r = ctx->replay;
-  cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream;
+  cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream, ps = r->pyr_stream;
 
   // the feature lists are small: upload them in one piece ahead of the pipeline
   RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
@@ -176,43 +184,43 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
   RCU(cudaStreamWaitEvent(xs, r->drained, 0));
   RCU(cudaStreamWaitEvent(os, r->drained, 0));
   RCU(cudaStreamWaitEvent(r->compute2, r->drained, 0));
+  RCU(cudaStreamWaitEvent(ps, r->drained, 0));
 
   const size_t dense_frame = (size_t)3 * w * h;
   int p0 = 0;
   for (int k = 0; p0 < npairs; ++k) {
-    const int b = k & 1, want = k == 0 ? first_chunk : chunk, c = npairs - p0 < want ? npairs - p0 : want;
+    const int b = k & 1, set = k % 3, want = k == 0 ? first_chunk : chunk, c = npairs - p0 < want ? npairs - p0 : want;
     cudaStream_t cs = b ? r->compute2 : cs0;
     // ---- copy stream: frames of chunk k into staging buffer b (free once chunk k-2's pyramids are built)
     if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
     rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride, c, xs);
     if (!rc)
-      rc = upload_frames(ctx, r->d_frames[b] + (size_t)chunk * dense_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
+      rc = upload_frames(ctx, r->d_frames[b] + (size_t)c * dense_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
                          row_stride, frame_stride, c, xs);
     if (rc) return rc;
     RCU(cudaEventRecord(r->copied[b], xs));
-    // ---- compute stream b: both pyramids, then forward/backward tracking of the chunk's features.  Stream order
-    // protects pyramid set b (chunk k-2 used the same stream); the work-queue counter is per stream.
-    RCU(cudaStreamWaitEvent(cs, r->copied[b], 0));
-    int nl = launch_pyr_build(r->pyr_from[b]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, c, cs);
-    if (nl >= 0) {
-      ctx->launches += nl;
-      nl = launch_pyr_build(r->pyr_to[b]->view, SFE_HESSIAN, r->d_frames[b] + (size_t)chunk * dense_frame, (size_t)3 * w,
-                            dense_frame, 0, c, cs);
-    }
+    // ---- pyramid stream: the pyramids of the chunk's frames into set k % 3 (free once chunk k-3 has been tracked)
+    RCU(cudaStreamWaitEvent(ps, r->copied[b], 0));
+    if (k >= 3) RCU(cudaStreamWaitEvent(ps, r->tracked[set], 0));
+    // one build for the 2c frames of the chunk: slots [0, c) the from-frames, [c, 2c) the to-frames
+    int nl = launch_pyr_build(r->pyr[set]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, 2 * c, ps);
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "pyramid launch", (cudaError_t)(-nl));
     ctx->launches += nl;
-    RCU(cudaEventRecord(r->consumed[b], cs));
+    RCU(cudaEventRecord(r->consumed[b], ps));
+    RCU(cudaEventRecord(r->built[set], ps));
+    // ---- compute stream b: forward/backward tracking of the chunk's features (the work-queue counter is per stream)
+    RCU(cudaStreamWaitEvent(cs, r->built[set], 0));
     const size_t f0 = (size_t)p0 * n_per_pair;
     const int nf = c * n_per_pair;
-    TrackArgs ta{nf, n_per_pair, 0, 0, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
+    TrackArgs ta{nf, n_per_pair, 0, c, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
                  thr, maxit, fb_max, r->d_back + 2 * f0, r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0, 2};
-    nl = launch_track_hessian(r->pyr_from[b]->view, r->pyr_to[b]->view, ta, ctx->d_mask, ctx->d_counter + 16 * (1 + b),
+    nl = launch_track_hessian(r->pyr[set]->view, r->pyr[set]->view, ta, ctx->d_mask, ctx->d_counter + 16 * (1 + b),
                               ctx->num_sms, cs);
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "track launch", (cudaError_t)(-nl));
     ctx->launches += nl;
-    RCU(cudaEventRecord(r->tracked[b], cs));
+    RCU(cudaEventRecord(r->tracked[set], cs));
     // ---- output stream: results of chunk k back to the caller's buffers
-    RCU(cudaStreamWaitEvent(os, r->tracked[b], 0));
+    RCU(cudaStreamWaitEvent(os, r->tracked[set], 0));
     RCU(cudaMemcpyAsync(to_xy + 2 * f0, r->d_to + 2 * f0, 8 * (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (back_xy) RCU(cudaMemcpyAsync(back_xy + 2 * f0, r->d_back + 2 * f0, 8 * (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (status_fwd) RCU(cudaMemcpyAsync(status_fwd + f0, r->d_s1 + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));

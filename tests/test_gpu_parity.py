@@ -195,10 +195,11 @@ def test_track_fb_batched_pairs(fe, po, synth):
 
 @pytest.mark.parametrize("chunk", [2, 0, 5])
 def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
-    """sfe_replay_pairs (host buffers, chunk-pipelined over three streams): 5 pairs in chunks of 2 (ragged last
-    chunk), automatic chunking and a single chunk -- every pair equals the single-pair oracle run bit for bit."""
+    """sfe_replay_pairs (host buffers, chunk-pipelined: copy | pyramid (three sets) | tracking | download streams):
+    9 pairs in chunks of 2 (five chunks, so every pyramid set and staging buffer is reused; ragged last chunk),
+    automatic chunking and chunks of 5 -- every pair equals the single-pair oracle run bit for bit."""
     H, W = 240, 320
-    npairs, npp = 5, 130
+    npairs, npp = 9, 130
     A, B = synth.make_pairs(33, npairs, H, W)
     A, B = A.numpy(), B.numpy()
     pts = np.concatenate([_features(synth, npp, H, W, seed=40 + p) for p in range(npairs)])
@@ -222,6 +223,7 @@ def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
     pB[...] = B
     g2 = fe.replay_pairs(pA, pB, pts, pts, depth=4, levels=lv, n_per_pair=npp, chunk_pairs=chunk)
     assert_bits_equal(g2["to_xy"], g["to_xy"], "pinned replay")
+    fe.sync()  # the asynchronous matcher runs on a side stream of the context: its results are valid after sfe_sync()
     oi, od, oo = po.hamming256_top2(hq, ht, 4, 5, 80)
     assert np.array_equal(out[0], oi) and np.array_equal(out[1], od) and np.array_equal(out[2], oo)
 
