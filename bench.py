@@ -45,6 +45,21 @@ def measured_traffic(kernel, batch):
         return None
 
 
+def issue_fraction(newton_steps, trk_ms, sms, clocks):
+    """Issue-slot utilisation of the tracking kernel: warp-instructions per second against 4 schedulers per SM x SM clock."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            per_step = float(json.load(f)["track_fb_kernel"]["ncu_warp_instructions_per_newton_step"])
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        achieved = per_step * newton_steps / (trk_ms * 1e-3)
+        peak = sms * 4 * mhz * 1e6
+        return {"bound": "instruction issue", "achieved": achieved, "peak": peak, "unit": "warp-instructions/s",
+                "frac": achieved / peak, "warp_instructions_per_newton_step": per_step,
+                "source": "profiles/track_r1h_summary.txt (ncu) x Newton steps counted by the kernel in this run"}
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -298,13 +313,17 @@ def run_gpu(args):
                          "peak": peak, "unit": "GB/s", "frac": trk_bytes / (trk_ms * 1e-3) / 1e9 / peak,
                          "traffic": measured_traffic("track_fb_kernel", B), "algorithmic_bytes": trk_bytes,
                          "peak_source": peak_src, "share_of_step": trk_ms / ms_step,
-                         "bilinear_samples_per_sec": newton * 6 * 169 / args.steps / 1.0 / (trk_ms * 1e-3) if False else
-                         (newton * 6 * 169) / (trk_ms * 1e-3)},
+                         "bilinear_samples_per_sec": (newton * 6 * 169) / (trk_ms * 1e-3),
+                         # what actually bounds it: instruction issue.  Executed warp-instructions per Newton step come
+                         # from the committed ncu capture of this kernel, the Newton steps are counted live by the kernel.
+                         "issue": issue_fraction(newton, trk_ms, torch.cuda.get_device_properties(dev).multi_processor_count,
+                                                 clocks)},
             # the HBM-streaming kernels of the path
             "roofline_pyramid": {"kernel": "pyr_row_kernel (levels 0+1 fused) + pyr_stream_kernel<down> x2, one build of 2B frames",
                                  "bound": "hbm",
                                  "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                 "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": measured_traffic("pyramid_build", B),
+                                 "algorithmic_bytes": pyr_bytes,
                                  "share_of_step": pyr_ms / ms_step},
         }
         if not args.no_cpu and world == 1:
