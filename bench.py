@@ -148,7 +148,7 @@ def make_inputs(torch, synth, batch, device, seed):
         Bs.append(b)
     A = torch.cat(As).contiguous()
     B = torch.cat(Bs).contiguous()
-    pts = np.concatenate([synth.make_features(seed * 7919 + p, NFEAT, H, W, margin=16.0) for p in range(batch)])
+    pts = np.concatenate([synth.make_features(seed * 7919 + p, NFEAT, H, W, margin=float(os.environ.get("SFE_BENCH_MARGIN", "16")))  for p in range(batch)])
     t = synth.make_descriptors(seed * 31 + 1, batch * NFEAT, dup_frac=0.001)
     q = synth.make_descriptors(seed * 31 + 2, batch * NFEAT, dup_frac=0.2, source=t)
     return A, B, pts.astype(np.float32), q, t
@@ -168,6 +168,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     fe = sfe.FrontEnd(local)

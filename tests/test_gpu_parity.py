@@ -44,7 +44,7 @@ def test_pyramid_1080p_8_levels_bit_exact(fe, po, synth):
 
 
 @pytest.mark.parametrize("shape,depth,nframes", [((480, 640), 4, 3), ((481, 640), 5, 2), ((97, 640), 3, 2), ((720, 1280), 6, 2),
-                                                 ((45, 1280), 2, 1), ((1080, 1920), 4, 1)])
+                                                 ((45, 1280), 2, 1), ((1080, 1920), 4, 1), ((16, 640), 2, 2), ((17, 640), 2, 1), ((18, 640), 3, 1)])
 def test_pyramid_row_kernel_bit_exact(fe, po, synth, shape, depth, nframes):
     """Widths of 640 / 1280 / 1920 columns take the row-CTA kernel (pyramid_stream.cu: one CTA per row band, neighbours
     through shared row buffers, lagged stages): odd heights, bands shorter than the pipeline fill, several bands."""
@@ -55,6 +55,23 @@ def test_pyramid_row_kernel_bit_exact(fe, po, synth, shape, depth, nframes):
         op = po.Pyramid(frames[f], depth, 0)
         for l in range(depth):
             assert_bits_equal(gp.plane(l, f), op.plane(l), "%dx%d frame %d level %d" % (W, H, f, l))
+
+
+def test_pyramid_build_into_slot_range_bit_exact(fe, po, synth):
+    """sfe_pyr_build with first != 0 (what sfe_replay_pairs and the bench's 2B-slot batch rely on): frames written into
+    slots [2, 5) of a batch of 6 leave the other slots alone and equal the oracle."""
+    H, W = 480, 640
+    frames = synth.make_frames(21, 6, H, W).numpy()
+    gp = fe.pyramid(W, H, 4, 0, 6)
+    gp.build(frames)
+    before = [gp.plane(l, 0).copy() for l in range(4)]
+    other = synth.make_frames(22, 3, H, W).numpy()
+    gp.build(other, first=2)
+    for l in range(4):
+        assert_bits_equal(gp.plane(l, 0), before[l], "slot 0 untouched, level %d" % l)
+        assert_bits_equal(gp.plane(l, 5), po.Pyramid(frames[5], 4, 0).plane(l), "slot 5 untouched, level %d" % l)
+        for f in range(3):
+            assert_bits_equal(gp.plane(l, 2 + f), po.Pyramid(other[f], 4, 0).plane(l), "slot %d level %d" % (2 + f, l))
 
 
 def test_pyramid_large_batch_single_band_bit_exact(fe, po, synth):
