@@ -48,6 +48,26 @@ struct WarpScratch {
   float mkT[SFE_SLOTS * 32];
 };
 
+// Per-lane patch coordinates, packed: byte k of (lo, hi) is pr * 16 + pc of the lane's slot k (i = lane + 32 k,
+// pr = i / 13, pc = i % 13) -- with the tile's row stride of 16 that byte IS the tap offset inside the footprint.
+// Two registers for the whole kernel instead of six quotients plus the multiply-subtract per slot and evaluation.
+struct PixPack {
+  unsigned lo, hi;
+};
+__device__ __forceinline__ PixPack make_pixpack(int lane) {
+  PixPack p{0u, 0u};
+#pragma unroll
+  for (int k = 0; k < SFE_SLOTS; ++k) {
+    const int i = lane + 32 * k;
+    const unsigned b = i < SFE_PLEN ? (unsigned)((i / SFE_PATCH) * TS + i % SFE_PATCH) : 0u;
+    if (k < 4) p.lo |= b << (8 * k); else p.hi |= b << (8 * (k - 4));
+  }
+  return p;
+}
+__device__ __forceinline__ int pix_off(const PixPack& p, int k) {   // zero-extended byte k: one PRMT
+  return (int)__byte_perm(k < 4 ? p.lo : p.hi, 0u, 0x4440u + (unsigned)(k & 3));
+}
+
 // x variants live in lanes 0..2 (p, p-h, p+h), y variants in lanes 4..6; BruteHessian's shifts
 // (0,0) (-h,0) (0,-h) (+h,0) (0,+h) (+h,+h) (hessian.h:154-161) pick variant (SXP>>2s)&3 / (SYP>>2s)&3.
 constexpr unsigned SXP = 0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 2u << 10;
@@ -87,7 +107,7 @@ __device__ __forceinline__ bool stage_tile(WarpScratch& S, const ImgView& im, in
 // B1' = vert ? 1-b : 1 the weights (A1'B1', aB1', A1'b, ab) reproduce the rule exactly (x*1 is exact
 // and a zero tap adds an exact zero), so one FMA chain serves all pixels.  Results go to S.v.
 __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im, const AxisGeom& g, int ox, int oy,
-                                               int nshift, bool shared_geom, int lane) {
+                                               int nshift, bool shared_geom, int lane, const PixPack& pix) {
   int toff[SFE_SLOTS];
   unsigned mx[SFE_SLOTS], mv[SFE_SLOTS];  // all-ones where the pixel uses x weights / vertical weights
 #pragma unroll 1
@@ -99,7 +119,7 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
         const int i = lane + 32 * k;
-        const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
+        const int po = pix_off(pix, k), pr = po >> 4, pc = po & 15;
         const bool valid = (k < SFE_SLOTS - 1 || i < SFE_PLEN) && pr >= ry && pc >= rx;
         const int X = x0 + pc, Y = y0 + pr;
         const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
@@ -129,14 +149,11 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
 // Plain route: no border rule and no clipping.  A compact runtime loop re-reads the 4 taps per shift, so it
 // also serves steps in which a +-h shift crosses an integer boundary (the shifts do not share their taps
 // then), template patches (one shift) and footprints that contain a zero.  Results go to S.v.
-__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int nshift, int lane) {
+__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int nshift, int lane,
+                                                const PixPack& pix) {
   int poff[SFE_SLOTS];
 #pragma unroll
-  for (int k = 0; k < SFE_SLOTS; ++k) {
-    const int i = lane + 32 * k;
-    const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-    poff[k] = (k < SFE_SLOTS - 1 || i < SFE_PLEN) ? pr * TS + pc : -1;
-  }
+  for (int k = 0; k < SFE_SLOTS; ++k) poff[k] = (k < SFE_SLOTS - 1 || lane + 32 * k < SFE_PLEN) ? pix_off(pix, k) : -1;
 #pragma unroll 1
   for (int s = 0; s < nshift; ++s) {
     const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
@@ -228,7 +245,8 @@ struct TileTag {
 //             d[6] = dx,dy,dxx,dxy,dyx,dyy (rounded to float as the reference stores them through
 //             float*); returns sad0.
 __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const ImgView im, bool is_tmpl, Tmpl& t,
-                                          const float* __restrict__ mask, float x, float y, int lane, float (&d)[6]) {
+                                          const float* __restrict__ mask, float x, float y, int lane, const PixPack& pix,
+                                          float (&d)[6]) {
   __syncwarp();
   const AxisGeom g = lane_geom(x, y, lane);
   const int ox = (int)floorf(x) - 7, oy = (int)floorf(y) - 7;
@@ -258,8 +276,8 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
   if (!fast) {
     int nshift = is_tmpl ? 1 : 6;
     asm volatile("" : "+r"(nshift));  // opaque: one copy of each loop serves both callers (code size)
-    if (plain) straddle_sample(S, g, ox, oy, nshift, lane);
-    else general_sample(S, im, g, ox, oy, nshift, differ == 0, lane);
+    if (plain) straddle_sample(S, g, ox, oy, nshift, lane, pix);
+    else general_sample(S, im, g, ox, oy, nshift, differ == 0, lane, pix);
   }
 
   if (is_tmpl) {
@@ -296,9 +314,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     const int base = (iy - oy) * TS + (ix - ox);
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
-      const int i = lane + 32 * k;
-      const int pr = i / SFE_PATCH, pc = i - pr * SFE_PATCH;
-      const float* tp = S.tile + ((k < SFE_SLOTS - 1 || i < SFE_PLEN) ? base + pr * TS + pc : ZOFF);
+      const float* tp = S.tile + ((k < SFE_SLOTS - 1 || lane + 32 * k < SFE_PLEN) ? base + pix_off(pix, k) : ZOFF);
       t00[k] = tp[0];
       t01[k] = tp[1];
       t10[k] = tp[TS];
@@ -400,7 +416,8 @@ __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
 // (hessian.h:185-241) on the search pyramid.  (x,y) is updated only on success.
 __device__ __forceinline__ int track_feature(WarpScratch& S, TileTag& tag, const PyrView& tp, int tframe, float tx, float ty,
                                              const PyrView& sp, int sframe, int levels, float thr, int maxit,
-                                             const float* __restrict__ mask, float& x, float& y, int lane, int& steps) {
+                                             const float* __restrict__ mask, float& x, float& y, int lane, const PixPack& pix,
+                                             int& steps) {
   const int lv = min(min(tp.depth, sp.depth), levels);
   const float margin = 0.01f;
   float px = x * (float)(1. / (1 << (lv - 1))), py = y * (float)(1. / (1 << (lv - 1)));
@@ -420,7 +437,7 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, TileTag& tag, const
       im.p = is_tmpl ? tim.p : sim.p;
       im.w = sim.w; im.h = sim.h; im.pitch = sim.pitch;  // both pyramids have the same geometry
       float d[6];
-      evaluate(S, tag, im, is_tmpl, t, mask, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, d);
+      evaluate(S, tag, im, is_tmpl, t, mask, is_tmpl ? tx * sc : px, is_tmpl ? ty * sc : py, lane, pix, d);
       if (is_tmpl) continue;
       ++steps;
       float dx, dy;
@@ -446,6 +463,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpScratch& S = scratch[warp];
   init_scratch(S, lane);
+  const PixPack pix = make_pixpack(lane);
 #pragma unroll 1
   for (;;) {
     int i = 0;
@@ -470,7 +488,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
       const PyrView& sp = dir == 0 ? to : from;
       float x = dir == 0 ? tx : bx, y = dir == 0 ? ty : by;
       const int s = track_feature(S, tag, tp, dir == 0 ? ff : tf, dir == 0 ? fx : tx, dir == 0 ? fy : ty, sp,
-                                  dir == 0 ? tf : ff, lv, a.thr, a.maxit, mask, x, y, lane, steps);
+                                  dir == 0 ? tf : ff, lv, a.thr, a.maxit, mask, x, y, lane, pix, steps);
       if (dir == 0) { tx = x; ty = y; st[0] = s; } else { bx = x; by = y; st[1] = s; }
     }
     bool ok = !(st[0] || st[1]);  // matcher.cpp:192
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) get_patches_kernel(PyrView v, 
   float d[6];
   Tmpl t;
   TileTag tag{nullptr, 0u};
-  evaluate(scratch[warp], tag, img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, d);
+  evaluate(scratch[warp], tag, img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, make_pixpack(lane), d);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
     if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = scratch[warp].T[k * 32 + lane];
@@ -522,8 +540,8 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) brute_hessian_kernel(PyrView t
   Tmpl t;
   float d[6];
   TileTag tag{nullptr, 0u};
-  evaluate(scratch[warp], tag, img_of(tv, 0, level, tframe), true, t, mask, txy[2 * i], txy[2 * i + 1], lane, d);
-  const float s0 = evaluate(scratch[warp], tag, img_of(sv, 0, level, sframe), false, t, mask, xy[2 * i], xy[2 * i + 1], lane, d);
+  evaluate(scratch[warp], tag, img_of(tv, 0, level, tframe), true, t, mask, txy[2 * i], txy[2 * i + 1], lane, make_pixpack(lane), d);
+  const float s0 = evaluate(scratch[warp], tag, img_of(sv, 0, level, sframe), false, t, mask, xy[2 * i], xy[2 * i + 1], lane, make_pixpack(lane), d);
   if (lane == 0) {
     out7[7 * i] = s0;
     for (int k = 0; k < 6; ++k) out7[7 * i + 1 + k] = d[k];
