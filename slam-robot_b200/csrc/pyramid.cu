@@ -446,7 +446,9 @@ int build_chunk(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_str
     int blur_id = flavor == SFE_HESSIAN ? 1 : (flavor == SFE_KLT ? 2 : -1);
     // fast path: blurred plane, both levels 4-float aligned, level at least one blur reach wide/high
     const bool fast_dn = blur_id >= 0 && v.w[l] % 4 == 0 && v.w[l - 1] % 4 == 0 && v.w[l] >= 8 && v.h[l] >= 8;
-    if (fast_dn && v.w[l] >= 256) launch_down_fast<64, 32>(v, l, first, count, blur_id, s);
+    // KLT / brute flavours: the strip-streaming down stage (pyramid_stream.cu) when the geometry qualifies
+    if (flavor != SFE_HESSIAN && launch_pyr_stream_down(v, 0, l, first, count, blur_id, 1.f, s)) {
+    } else if (fast_dn && v.w[l] >= 256) launch_down_fast<64, 32>(v, l, first, count, blur_id, s);
     else if (fast_dn) launch_down_fast<32, 16>(v, l, first, count, blur_id, s);
     else
       pyr_down_kernel<<<g, DN_THREADS, 0, s>>>(v.base[0][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1],
@@ -455,6 +457,10 @@ int build_chunk(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_str
     ++launches;
     if (flavor == SFE_KLT) {
       for (int p = 1; p <= 2; ++p) {  // klt.h:123-124
+        if (launch_pyr_stream_down(v, p, l, first, count, -1, 2.f, s)) {
+          ++launches;
+          continue;
+        }
         pyr_down_kernel<<<g, DN_THREADS, 0, s>>>(v.base[p][l - 1], v.frame_stride[l - 1], v.w[l - 1], v.h[l - 1],
                                                  v.pitch[l - 1], v.base[p][l], v.frame_stride[l], v.w[l],
                                                  v.h[l], v.pitch[l], first, -1, 2.f);

@@ -43,6 +43,7 @@ struct StreamArgs {
   int w1, h1;              // size of the downsampled level: w/2, (h+1)/2
   int first;               // first frame slot in the pyramid batch
   int strips, bands, band_rows, nunits;
+  float scale;             // DOWN_ONLY: factor applied to the pyrDown result (klt.h:123-124 doubles the gradients)
 };
 
 __device__ __forceinline__ float gray_px(uint32_t p) {
@@ -87,7 +88,9 @@ __device__ __forceinline__ void issue_row(uint32_t slot_addr, const StreamArgs& 
 // One warp = one (frame, row band, column strip) unit.
 // BLUR0 / BLUR1 select the Gaussian tap sets at compile time: as immediates the taps let FMUL/FFMA issue at the full
 // rate (the three-register forms issue every other cycle, and this kernel is FP-pipe bound).
-template <bool FROM_BGR, int BLUR0, int BLUR1>
+// DOWN_ONLY (with !FROM_BGR): the level is the bare pyrDown of its input times a.scale -- the gradient planes of klt.h
+// (:123-124) and every level of brute.h (:72-77); the blur stage is skipped and the pyrDown row itself is stored.
+template <bool FROM_BGR, int BLUR0, int BLUR1, bool DOWN_ONLY = false>
 __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   const int lane = threadIdx.x;
   const int unit = blockIdx.x;
@@ -194,6 +197,11 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         const float2 pab = pd_v2(p0, p1, p2, p3, p4);
         const float pa = pab.x, pb = pab.y;
         const int i = (q - 2) >> 1;
+        if constexpr (DOWN_ONLY) {
+          if (useful && i >= j_lo && i < j_hi)
+            *reinterpret_cast<float2*>(out1_px + (size_t)i * a.out1_pitch) = make_float2(pa * a.scale, pb * a.scale);
+          continue;
+        }
         // GaussianBlur rows on the pyrDown row: columns c0-2, c0-1 from the left lane, c0+2, c0+3 from the right lane
         float la = __shfl_up_sync(SFE_FULL, pa, 1), lb = __shfl_up_sync(SFE_FULL, pb, 1);
         float ra = __shfl_down_sync(SFE_FULL, pa, 1), rb = __shfl_down_sync(SFE_FULL, pb, 1);
@@ -521,4 +529,25 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
     built = l + 1;
   }
   return built;
+}
+
+// One down stage of ONE plane by the strip kernel, for the flavours whose levels are not all "pyrDown + sigma-0.8 blur":
+// blur_id 1 / 2 = pyrDown then GaussianBlur sigma 0.8 / 0.6 (klt.h:117-118), blur_id < 0 = bare pyrDown times `scale`
+// (klt.h:123-124 gradients, brute.h:72-77).  Returns 1 when launched, 0 when the geometry does not qualify (the caller
+// then uses the tiled kernel).
+int launch_pyr_stream_down(const PyrView& v, int plane, int l, int first, int count, int blur_id, float scale, cudaStream_t s) {
+  static const bool tiled_only = getenv("SFE_PYR_TILED") != nullptr;
+  if (tiled_only || l < 1 || v.w[l - 1] % 4 != 0 || v.w[l - 1] < 16 || v.h[l - 1] < 16 || blur_id == 0 || blur_id > 2) return 0;
+  StreamArgs a{};
+  a.w = v.w[l - 1]; a.h = v.h[l - 1]; a.w1 = v.w[l]; a.h1 = v.h[l];
+  a.first = first;
+  a.strips = (a.w + STRIP_USEFUL - 1) / STRIP_USEFUL;
+  a.in = v.base[plane][l - 1]; a.in_fs = v.frame_stride[l - 1]; a.in_pitch = v.pitch[l - 1];
+  a.out1 = v.base[plane][l]; a.out1_fs = v.frame_stride[l]; a.out1_pitch = v.pitch[l];
+  a.scale = scale;
+  plan_bands<false>(a, count);
+  if (blur_id == 1) pyr_stream_kernel<false, 0, 1><<<a.nunits, 32, 0, s>>>(a);
+  else if (blur_id == 2) pyr_stream_kernel<false, 0, 2><<<a.nunits, 32, 0, s>>>(a);
+  else pyr_stream_kernel<false, 0, 1, true><<<a.nunits, 32, 0, s>>>(a);
+  return 1;
 }
