@@ -146,6 +146,53 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
   }
 }
 
+// General route when all shifts share their integer geometry (the usual case: no +-h shift crosses an integer
+// boundary).  Slots outside, shifts inside: a pixel's taps, its border masks and its three A1' / B1' candidates are
+// formed ONCE and serve all six shifts, whose weights differ only in which axis variant they take -- 4 loads and the
+// border logic per pixel instead of per pixel and shift.  The loop over the slots is rolled (code size), the six
+// shifts inside are unrolled with compile-time variant indices.
+__device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgView& im, const AxisGeom& g, int ox, int oy,
+                                                      int nshift, int lane, const PixPack& pix) {
+  const int x0 = __shfl_sync(SFE_FULL, g.i0, 0), rx = __shfl_sync(SFE_FULL, g.r, 0);
+  const int y0 = __shfl_sync(SFE_FULL, g.i0, 4), ry = __shfl_sync(SFE_FULL, g.r, 4);
+  float ax[3], ay[3];
+  unsigned ax1[3], ay1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    ax[j] = __shfl_sync(SFE_FULL, g.a, j);
+    ax1[j] = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, j));
+    ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
+    ay1[j] = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, 4 + j));
+  }
+  const unsigned one = 0x3f800000u;
+#pragma unroll 1
+  for (int k = 0; k < SFE_SLOTS; ++k) {
+    const int po = (int)(((k < 4 ? pix.lo : pix.hi) >> (8 * (k & 3))) & 0xffu), pr = po >> 4, pc = po & 15;
+    const bool valid = lane + 32 * k < SFE_PLEN && pr >= ry && pc >= rx;
+    const int X = x0 + pc, Y = y0 + pr;
+    const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
+    int Xq = X;
+    if (!xin && !yin && Y < 0 && X >= im.w - 1 && im.w >= 2) Xq = im.w - 2;  // OpenCV top-right quirk
+    const float* t = S.tile + (valid ? clampi(Y - oy, 0, 14) * TS + clampi(Xq - ox, 0, 14) : ZOFF);
+    const unsigned mx = xin ? 0xffffffffu : 0u, mv = (yin || !xin) ? 0xffffffffu : 0u;
+    const float t00 = t[0], t01 = __uint_as_float(__float_as_uint(t[1]) & mx);
+    const float t10 = __uint_as_float(__float_as_uint(t[TS]) & mv), t11 = __uint_as_float(__float_as_uint(t[TS + 1]) & mx & mv);
+    float A1[3], B1[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      A1[j] = __uint_as_float((ax1[j] & mx) | (one & ~mx));
+      B1[j] = __uint_as_float((ay1[j] & mv) | (one & ~mv));
+    }
+    float* out = S.v + k * 32 + lane;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      if (s == 1 && nshift == 1) break;   // template patch: shift 0 only
+      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
+      out[s * SFE_SLOTS * 32] = fmaf(t11, ax[jx] * ay[jy], fmaf(t10, A1[jx] * ay[jy], fmaf(t01, ax[jx] * B1[jy], t00 * (A1[jx] * B1[jy]))));
+    }
+  }
+}
+
 // Plain route: no border rule and no clipping.  A compact runtime loop re-reads the 4 taps per shift, so it
 // also serves steps in which a +-h shift crosses an integer boundary (the shifts do not share their taps
 // then), template patches (one shift) and footprints that contain a zero.  Results go to S.v.
@@ -277,7 +324,8 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     int nshift = is_tmpl ? 1 : 6;
     asm volatile("" : "+r"(nshift));  // opaque: one copy of each loop serves both callers (code size)
     if (plain) straddle_sample(S, g, ox, oy, nshift, lane, pix);
-    else general_sample(S, im, g, ox, oy, nshift, differ == 0, lane, pix);
+    else if (differ == 0) general_sample_shared(S, im, g, ox, oy, nshift, lane, pix);
+    else general_sample(S, im, g, ox, oy, nshift, false, lane, pix);
   }
 
   if (is_tmpl) {
