@@ -55,7 +55,7 @@ def issue_fraction(newton_steps, trk_ms, sms, clocks):
         peak = sms * 4 * mhz * 1e6
         return {"bound": "instruction issue", "achieved": achieved, "peak": peak, "unit": "warp-instructions/s",
                 "frac": achieved / peak, "warp_instructions_per_newton_step": per_step,
-                "source": "profiles/track_r1h_summary.txt (ncu) x Newton steps counted by the kernel in this run"}
+                "source": "profiles/track_r1i_summary.txt (ncu) x Newton steps counted by the kernel in this run"}
     except Exception:
         return None
 
