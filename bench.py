@@ -148,7 +148,10 @@ def make_inputs(torch, synth, batch, device, seed):
         Bs.append(b)
     A = torch.cat(As).contiguous()
     B = torch.cat(Bs).contiguous()
-    pts = np.concatenate([synth.make_features(seed * 7919 + p, NFEAT, H, W, margin=float(os.environ.get("SFE_BENCH_MARGIN", "16")))  for p in range(batch)])
+    # SFE_BENCH_MARGIN (experiments only): minimum distance of the features from the image border; 70 keeps every patch
+    # of every level inside the image, which is how the cost of the border route was measured (profiles/README.md)
+    margin = float(os.environ.get("SFE_BENCH_MARGIN", "16"))
+    pts = np.concatenate([synth.make_features(seed * 7919 + p, NFEAT, H, W, margin=margin) for p in range(batch)])
     t = synth.make_descriptors(seed * 31 + 1, batch * NFEAT, dup_frac=0.001)
     q = synth.make_descriptors(seed * 31 + 2, batch * NFEAT, dup_frac=0.2, source=t)
     return A, B, pts.astype(np.float32), q, t
