@@ -91,6 +91,24 @@ def test_pyramid_large_batch_single_band_bit_exact(fe, po, synth):
             assert_bits_equal(gp.plane(l, f), op.plane(l), "frame %d level %d" % (f, l))
 
 
+def test_pyramid_row_kernel_band_split_invariance(fe, synth):
+    """The same 96 frames built in one call (few row bands per frame) and in calls of 8 frames (many short bands per
+    frame, different CTA interleaving) must give bit-identical pyramids: the band overlap, the lagged shared-memory
+    exchange and its barriers cannot depend on how the frames are cut (a race would show up as a flaky mismatch)."""
+    import torch
+    H, W, n = 480, 640, 96
+    frames = torch.cat([synth.make_frames(31 + i, 32, H, W, device="cuda") for i in range(n // 32)]).contiguous()
+    g1 = fe.pyramid(W, H, 4, 0, n)
+    g2 = fe.pyramid(W, H, 4, 0, n)
+    for rep in range(3):
+        g1.build(frames)
+        for f0 in range(0, n, 8):
+            g2.build(frames[f0:f0 + 8].contiguous(), first=f0)
+        for f in range(0, n, 5):
+            for l in range(4):
+                assert_bits_equal(g1.plane(l, f), g2.plane(l, f), "rep %d frame %d level %d" % (rep, f, l))
+
+
 def _features(synth, n, H, W, seed=5, border=0.2):
     return synth.make_features(seed, n, H, W, margin=16, border_frac=border)
 
