@@ -95,21 +95,58 @@ int track_host(sfe_ctx* ctx, int n, const float* from_xy, float* to_xy, const in
   size_t need = padded(8 * (size_t)n) * 3 + padded(4 * (size_t)n) * 4 + padded(n);
   int rc = ensure_scratch(ctx, need);
   if (rc) return rc;
+  // inputs first (from, levels, seeds), then the outputs (to, back, statuses, steps, accepted): each group is one
+  // contiguous range of the scratch
   Carver c{(char*)ctx->scratch, 0};
   float* d_from = c.take<float>(2 * (size_t)n);
-  float* d_to = c.take<float>(2 * (size_t)n);
-  float* d_back = c.take<float>(2 * (size_t)n);
   int32_t* d_lv = c.take<int32_t>(n);
+  float* d_to = c.take<float>(2 * (size_t)n);
+  const size_t in_bytes = c.off;
+  float* d_back = c.take<float>(2 * (size_t)n);
   int32_t* d_s1 = c.take<int32_t>(n);
   int32_t* d_s2 = c.take<int32_t>(n);
   int32_t* d_steps = c.take<int32_t>(n);
   uint8_t* d_acc = c.take<uint8_t>(n);
+  const size_t out_off = (char*)d_to - (char*)ctx->scratch, out_bytes = c.off - out_off;
   cudaStream_t s = ctx->stream;
-  CU(cudaMemcpyAsync(d_from, from_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(d_to, to_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
-  if (levels) CU(cudaMemcpyAsync(d_lv, levels, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  // Small calls (the live robot tracks a few hundred features per frame, matcher.cpp:208-271) are latency-bound: nine
+  // copies of a few KB from pageable memory cost more than the kernel.  They go through a pinned mirror of the scratch
+  // head instead -- one upload, one download -- and are scattered to the caller's arrays on the host.
+  const bool staged = n <= 65536;
+  if (staged) {
+    if (c.off > ctx->h_stage_cap) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr;
+      ctx->h_stage_cap = 0;
+      cudaError_t e = cudaMallocHost(&ctx->h_stage, c.off);
+      if (e != cudaSuccess) return fail(ctx, SFE_ERR_NOMEM, "cudaMallocHost(staging): %s", cudaGetErrorString(e));
+      ctx->h_stage_cap = c.off;
+    }
+    char* h = (char*)ctx->h_stage;
+    memcpy(h + ((char*)d_from - (char*)ctx->scratch), from_xy, 8 * (size_t)n);
+    if (levels) memcpy(h + ((char*)d_lv - (char*)ctx->scratch), levels, 4 * (size_t)n);
+    memcpy(h + out_off, to_xy, 8 * (size_t)n);
+    CU(cudaMemcpyAsync(ctx->scratch, h, in_bytes, cudaMemcpyHostToDevice, s));
+  } else {
+    CU(cudaMemcpyAsync(d_from, from_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_to, to_xy, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    if (levels) CU(cudaMemcpyAsync(d_lv, levels, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  }
   rc = launch(d_from, d_to, levels ? d_lv : nullptr, d_back, d_s1, d_s2, d_acc, d_steps);
   if (rc) return rc;
+  if (staged) {
+    char* h = (char*)ctx->h_stage;
+    CU(cudaMemcpyAsync(h + out_off, d_to, out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    auto at = [&](const void* d) { return h + ((const char*)d - (const char*)ctx->scratch); };
+    memcpy(to_xy, at(d_to), 8 * (size_t)n);
+    if (back_xy) memcpy(back_xy, at(d_back), 8 * (size_t)n);
+    if (status_fwd) memcpy(status_fwd, at(d_s1), 4 * (size_t)n);
+    if (status_bwd) memcpy(status_bwd, at(d_s2), 4 * (size_t)n);
+    if (accepted) memcpy(accepted, at(d_acc), (size_t)n);
+    if (steps) memcpy(steps, at(d_steps), 4 * (size_t)n);
+    return SFE_SUCCESS;
+  }
   CU(cudaMemcpyAsync(to_xy, d_to, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
   if (back_xy) CU(cudaMemcpyAsync(back_xy, d_back, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
   if (status_fwd) CU(cudaMemcpyAsync(status_fwd, d_s1, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -179,6 +216,7 @@ void sfe_destroy(sfe_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   sfe_replay_release(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
   if (ctx->ham_stream) {
     cudaStreamSynchronize(ctx->ham_stream);

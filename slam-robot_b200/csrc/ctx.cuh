@@ -15,6 +15,8 @@ struct sfe_ctx {
   // grow-on-demand device scratch for the host-pointer entry points
   void* scratch;
   size_t scratch_cap;
+  void* h_stage;   // pinned host mirror of the scratch head: small host-pointer calls move their arrays in two copies
+  size_t h_stage_cap;
   void* ham_ws;
   size_t ham_cap;
   void* ham_io;   // device buffers of sfe_match_hamming256_async (must outlive the call, so not the shared scratch)
