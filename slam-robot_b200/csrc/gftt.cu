@@ -233,17 +233,120 @@ __device__ __forceinline__ void bitonic_chunk(unsigned long long* sk, int chunk_
     }
 }
 
+// Greedy minimum-distance selection (featureselect.cpp) over the first `n` keys of the descending list `list`: a
+// candidate is kept unless an accepted corner lies closer than min_distance.  Sequential by nature; warp 0 walks the
+// candidates and tests each against the accepted corners 32 at a time.  Returns the number of corners (in every lane).
+__device__ __forceinline__ int greedy_select(const SelArgs& a, const unsigned long long* list, int n, float* acc, float* out, int lane) {
+  const bool check = a.min_distance >= 1.0;
+  const double md2 = a.min_distance * a.min_distance;
+  int cnt = 0;
+  for (int c = 0; c < n && cnt < a.max_corners; ++c) {
+    const unsigned ofs = (unsigned)list[c];
+    const int y = ofs / a.w, x = ofs - y * a.w;
+    bool bad = false;
+    if (check)
+      for (int k = lane; k < cnt; k += 32) {
+        const float dx = (float)x - acc[2 * k], dy = (float)y - acc[2 * k + 1];
+        bad |= (double)(dx * dx + dy * dy) < md2;
+      }
+    if (__any_sync(SFE_FULL, bad)) continue;
+    if (lane == 0) {
+      acc[2 * cnt] = (float)x;
+      acc[2 * cnt + 1] = (float)y;
+      out[2 * cnt] = (float)x;
+      out[2 * cnt + 1] = (float)y;
+    }
+    ++cnt;
+    __syncwarp();
+  }
+  return cnt;
+}
+
+// The selection stops after max_corners corners, which on a textured frame takes the first few hundred of ~20 000
+// candidates -- sorting all of them is most of a single frame's latency.  So the kernel first tries a PREFIX: a
+// histogram over 12 bits of the response code (exponent + 4 mantissa bits, 16 bins per octave) finds the cut bin above
+// which about SEL_TOPK candidates lie; only those are compacted into shared memory, sorted and fed to the greedy
+// selection.  If that yields max_corners corners the result is, by construction, the one the full list gives (the
+// prefix of a descending list does not depend on what follows it).  Otherwise -- few strong corners, a large
+// max_corners -- the kernel falls back to sorting everything.
+constexpr int SEL_TOPK = 1024;
+constexpr int SEL_BINS = 4096;
+__device__ __forceinline__ int sel_bin(unsigned long long key) { return (int)((key >> (32 + 19)) & (SEL_BINS - 1)); }
+
 __global__ void __launch_bounds__(SEL_THREADS) gftt_select_kernel(const SelArgs a) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   float* acc = reinterpret_cast<float*>(sel_smem);                                                    // [max_corners][2]
   unsigned long long* sk = reinterpret_cast<unsigned long long*>(sel_smem + ((8 * (size_t)a.max_corners + 15) & ~(size_t)15));
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_hist[SEL_BINS];
+  __shared__ int s_warp[SEL_THREADS / 32];
+  __shared__ int s_cut, s_m, s_cnt;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   unsigned long long* keys = a.keys + (size_t)frame * a.cap;
+  float* out = a.corners + (size_t)frame * a.max_corners * 2;
   if (a.ncand[frame] > a.cap) {  // candidate list overflowed: report instead of returning a wrong list
     if (tid == 0) a.ncorners[frame] = -1;
     return;
   }
   const int n = a.ncand[frame];
+
+  // ---- prefix attempt
+  if (n > 4 * SEL_TOPK) {
+    for (int i = tid; i < SEL_BINS; i += SEL_THREADS) s_hist[i] = 0;
+    if (tid == 0) { s_cut = 0; s_m = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += SEL_THREADS) atomicAdd(&s_hist[sel_bin(keys[i])], 1);
+    __syncthreads();
+    // suffix sums from the top bin: thread t owns bins 4t..4t+3 counted from the top
+    int own[4], mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { own[q] = s_hist[SEL_BINS - 1 - (4 * tid + q)]; mine += own[q]; }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(SFE_FULL, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < (tid >> 5); ++w) before += s_warp[w];
+    int run = before + incl - mine;   // candidates in the bins above this thread's
+    if (run < SEL_TOPK) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int prev = run;
+        run += own[q];
+        if (prev < SEL_TOPK && run >= SEL_TOPK) s_cut = SEL_BINS - 1 - (4 * tid + q);   // exactly one thread and bin
+      }
+    }
+    __syncthreads();
+    const int cut = s_cut;   // 0 when all candidates together are fewer than SEL_TOPK: everything passes
+    for (int i = tid; i < n; i += SEL_THREADS) {
+      const unsigned long long k = keys[i];
+      if (sel_bin(k) >= cut) {
+        const int pos = atomicAdd(&s_m, 1);
+        if (pos < SEL_CHUNK) sk[pos] = k;
+      }
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m <= SEL_CHUNK) {
+      int mp2 = 1;
+      while (mp2 < m) mp2 <<= 1;
+      for (int i = m + tid; i < mp2; i += SEL_THREADS) sk[i] = 0ull;
+      __syncthreads();
+      bitonic_chunk(sk, 0, mp2, 2, mp2, mp2, tid);
+      if (tid < 32) {
+        const int cnt = greedy_select(a, sk, m, acc, out, lane);
+        if (tid == 0) s_cnt = cnt;
+      }
+      __syncthreads();
+      if (s_cnt >= a.max_corners || m == n) {
+        if (tid == 0) a.ncorners[frame] = s_cnt;
+        return;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- the whole list
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   for (int i = n + tid; i < np2; i += SEL_THREADS) keys[i] = 0ull;  // pad: sorts to the end (descending)
@@ -276,33 +379,8 @@ __global__ void __launch_bounds__(SEL_THREADS) gftt_select_kernel(const SelArgs 
       __syncthreads();
     }
   }
-  // greedy selection (featureselect.cpp): a candidate is kept unless an accepted corner lies closer than
-  // min_distance.  Sequential by nature; one warp walks the sorted candidates and tests each against the
-  // accepted corners 32 at a time.
   if (tid >= 32) return;
-  float* out = a.corners + (size_t)frame * a.max_corners * 2;
-  const bool check = a.min_distance >= 1.0;
-  const double md2 = a.min_distance * a.min_distance;
-  int cnt = 0;
-  for (int c = 0; c < n && cnt < a.max_corners; ++c) {
-    const unsigned ofs = (unsigned)keys[c];
-    const int y = ofs / a.w, x = ofs - y * a.w;
-    bool bad = false;
-    if (check)
-      for (int k = tid; k < cnt; k += 32) {
-        const float dx = (float)x - acc[2 * k], dy = (float)y - acc[2 * k + 1];
-        bad |= (double)(dx * dx + dy * dy) < md2;
-      }
-    if (__any_sync(SFE_FULL, bad)) continue;
-    if (tid == 0) {
-      acc[2 * cnt] = (float)x;
-      acc[2 * cnt + 1] = (float)y;
-      out[2 * cnt] = (float)x;
-      out[2 * cnt + 1] = (float)y;
-    }
-    ++cnt;
-    __syncwarp();
-  }
+  const int cnt = greedy_select(a, keys, n, acc, out, lane);
   if (tid == 0) a.ncorners[frame] = cnt;
 }
 
@@ -324,7 +402,7 @@ int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_str
   const size_t smem = ((sizeof(float) * 2 * (size_t)max_corners + 15) & ~(size_t)15) + sizeof(unsigned long long) * SEL_CHUNK;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gftt_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(gftt_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // + 17 KB static (histogram) stays under 227 KB
     attr = true;
   }
   gftt_select_kernel<<<count, SEL_THREADS, smem, s>>>(sa);
