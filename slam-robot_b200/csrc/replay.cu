@@ -174,17 +174,19 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
   sfe_replay* r = ctx->replay;
   cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream, ps = r->pyr_stream;
 
-  // the feature lists are small: upload them in one piece ahead of the pipeline
-  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
-  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
-  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs0));
   // the other streams must not run ahead of whatever the caller queued on the context's stream before this call
   // (which also covers the staging buffers of a previous call)
   RCU(cudaEventRecord(r->drained, cs0));
   RCU(cudaStreamWaitEvent(xs, r->drained, 0));
   RCU(cudaStreamWaitEvent(os, r->drained, 0));
-  RCU(cudaStreamWaitEvent(r->compute2, r->drained, 0));
   RCU(cudaStreamWaitEvent(ps, r->drained, 0));
+  // the feature lists are small: upload them in one piece on the context's stream, while the copy stream already
+  // brings in the first chunk's frames; the second compute stream waits for them through `drained` re-recorded below
+  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
+  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
+  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs0));
+  RCU(cudaEventRecord(r->drained, cs0));
+  RCU(cudaStreamWaitEvent(r->compute2, r->drained, 0));
 
   const size_t dense_frame = (size_t)3 * w * h;
   int p0 = 0;
