@@ -328,6 +328,9 @@ def run_gpu(args):
                                  "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": measured_traffic("pyramid_build", B),
                                  "algorithmic_bytes": pyr_bytes,
+                                 "note": "write-bound: the build writes 1.6x what it reads; write-only HBM traffic reaches 3.9 TB/s and a "
+                                         "5 read : 8 write mix 5.5 TB/s on this GPU (tools/hbm_mix_probe.py), against 6.5 TB/s for the copy "
+                                         "that defines `peak`",
                                  "share_of_step": pyr_ms / ms_step},
         }
         if not args.no_cpu and world == 1:
