@@ -201,8 +201,8 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
  * (matcher.cpp:317) and the FindMatches tracking loop (matcher.cpp:208-271 -> :173-206) -- for
  * `npairs` independent (from, to) frame pairs of a replayed sequence (BASELINE config 4), host
  * buffers in and out.  The pairs are processed in chunks of `chunk_pairs` (<= 0: automatic) on a
- * three-stream pipeline (upload of chunk k+1 | pyramids + tracking of chunk k | download of chunk
- * k-1), so with pinned host buffers the PCIe transfers hide behind the kernels.
+ * stream pipeline (upload of chunk k+2 | pyramids of chunk k+1 | tracking of chunk k | download of
+ * chunk k-1), so with pinned host buffers the PCIe transfers hide behind the kernels.
  *   from_bgr, to_bgr  npairs frames each, 8-bit BGR, row_stride / frame_stride in bytes
  *   feature arrays    npairs * n_per_pair entries, pair-major, semantics of sfe_track_fb
  * Returns after all results are in the caller's buffers. */
@@ -211,6 +211,18 @@ int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const ui
                      const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
                      float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
                      int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
+
+/* The same pipeline for a replayed SEQUENCE (`./slam --load dir`, main.cpp:446-448): `nframes` consecutive frames in one
+ * buffer, pair i = (frame i, frame i + pair_stride) for i < nframes - pair_stride (the reference's two cameras alternate,
+ * so same-camera pairs are pair_stride = 2 apart).  Every frame is uploaded and its pyramid built once per chunk it
+ * belongs to -- as Matcher::Track builds one pyramid per new frame (matcher.cpp:317) -- instead of once as a `from` and
+ * once as a `to` frame.  Feature arrays: (nframes - pair_stride) * n_per_pair entries, pair-major.  Results are
+ * identical to sfe_replay_pairs on the pairs spelled out. */
+int sfe_replay_sequence(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
+                        const uint8_t* frames_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+                        const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                        float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                        int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
 
 /* ---- corner seeding (the step after tracking on keyframes) -------------------------------- */
 

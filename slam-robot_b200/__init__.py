@@ -32,7 +32,7 @@ EXPORTS = [
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
-    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_good_features", "sfe_good_features_dev",
+    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_good_features", "sfe_good_features_dev",
     "sfe_seed_features", "sfe_seed_features_dev", "sfe_yuyv_to_bgr", "sfe_yuyv_to_bgr_dev",
 ]
 
@@ -121,6 +121,8 @@ def lib():
     L.sfe_yuyv_to_bgr_dev.argtypes = [vp, vp, sz, vp]
     L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
                                    vp, vp, i32]
+    L.sfe_replay_sequence.argtypes = [vp, i32, i32, i32, i32, i32, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
+                                      vp, vp, i32]
     _lib = L
     return L
 
@@ -355,6 +357,32 @@ class FrontEnd:
                                           _ptr(from_xy), _ptr(to_xy), _ptr(lv_arr), int(levels) if lv_arr is None else 3, thr,
                                           maxit, fb_max, _ptr(out["back_xy"]), _ptr(out["status_fwd"]), _ptr(out["status_bwd"]),
                                           _ptr(out["accepted"]), _ptr(out.get("steps")), int(chunk_pairs)))
+        return out
+
+    def replay_sequence(self, frames, pair_stride, from_xy, seed_xy, depth, levels=3, thr=0.001, maxit=10, fb_max=0.3,
+                        n_per_pair=None, chunk_pairs=0, out=None, want_steps=True):
+        """frames: (nframes,H,W,3) uint8 host array of a replayed sequence; pair i = (frame i, frame i + pair_stride).
+        from_xy/seed_xy: ((nframes - pair_stride) * n_per_pair, 2) float32 host arrays, pair-major."""
+        nframes, H, W, ch = frames.shape
+        npairs = max(nframes - int(pair_stride), 0)
+        assert ch == 3 and (frames.is_contiguous() if _is_torch(frames) else frames.flags.c_contiguous)
+        from_xy = from_xy if _is_torch(from_xy) else _np(from_xy, np.float32).reshape(-1, 2)
+        n = from_xy.shape[0]
+        npp = n // max(npairs, 1) if n_per_pair is None else int(n_per_pair)
+        assert npp * npairs == n
+        if out is None:
+            out = dict(to_xy=np.empty((n, 2), np.float32), back_xy=np.empty((n, 2), np.float32), status_fwd=np.empty(n, np.int32),
+                       status_bwd=np.empty(n, np.int32), accepted=np.empty(n, np.uint8),
+                       steps=np.empty(n, np.int32) if want_steps else None)
+        out["to_xy"][...] = np.asarray(seed_xy, np.float32).reshape(-1, 2)
+        lv_arr = None
+        if levels is not None and not np.isscalar(levels):
+            lv_arr = _np(levels, np.int32)
+        self._chk(self.L.sfe_replay_sequence(self.h, W, H, depth, nframes, int(pair_stride), _ptr(frames), 3 * W, 3 * W * H,
+                                             max(npp, 1), _ptr(from_xy), _ptr(out["to_xy"]), _ptr(lv_arr),
+                                             int(levels) if lv_arr is None else 3, thr, maxit, fb_max, _ptr(out["back_xy"]),
+                                             _ptr(out["status_fwd"]), _ptr(out["status_bwd"]), _ptr(out["accepted"]),
+                                             _ptr(out.get("steps")), int(chunk_pairs)))
         return out
 
     # ---- corner seeding (matcher.cpp:313 + :123-130: RGB2GRAY + goodFeaturesToTrack)

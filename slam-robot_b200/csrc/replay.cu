@@ -151,15 +151,21 @@ void sfe_replay_release(sfe_ctx* ctx) {
   ctx->replay = nullptr;
 }
 
-extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
-                                const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
-                                const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
-                                int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
-                                uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+namespace {
+// The pipeline behind both entry points.  seq_stride == 0: independent pairs, pair i = (from_bgr[i], to_bgr[i]).
+// seq_stride > 0: a replayed SEQUENCE in from_bgr (to_bgr unused), pair i = (frame i, frame i + seq_stride) -- a chunk of c
+// pairs then needs the c + seq_stride consecutive frames [p0, p0 + c + seq_stride), which are uploaded and built once
+// (the reference builds one pyramid per new frame, matcher.cpp:317), not once as a `from` and once as a `to` frame.
+int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride, const uint8_t* from_bgr,
+               const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+               const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
+               int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+               uint8_t* accepted, int32_t* steps, int chunk_pairs) {
   if (!ctx) return SFE_ERR_INVALID;
   if (npairs == 0) return SFE_SUCCESS;
-  if (w < 1 || h < 1 || depth < 1 || depth > SFE_MAX_LEVELS || npairs < 0 || n_per_pair < 1 || !from_bgr || !to_bgr ||
-      !from_xy || !to_xy || default_levels < 1 || maxit < 0 || row_stride < (size_t)3 * w)
+  if (w < 1 || h < 1 || depth < 1 || depth > SFE_MAX_LEVELS || npairs < 0 || n_per_pair < 1 || !from_bgr ||
+      (seq_stride == 0 && !to_bgr) || seq_stride < 0 || !from_xy || !to_xy || default_levels < 1 || maxit < 0 ||
+      row_stride < (size_t)3 * w)
     return rfail(ctx, SFE_ERR_INVALID, "bad arguments", cudaSuccess);
   RCU(cudaSetDevice(ctx->device));
   // chunk size: default = an eighth of the batch (at least 8 pairs so that the kernels still fill the GPU; measured
@@ -167,6 +173,7 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
   int chunk = chunk_pairs > 0 ? chunk_pairs : (npairs + 7) / 8;
   if (chunk_pairs <= 0 && chunk < 8) chunk = 8;
   if (chunk > npairs) chunk = npairs;
+  if (chunk < seq_stride) chunk = seq_stride;   // a chunk's c + seq_stride frames must fit the 2 * chunk staging slots
   const int first_chunk = chunk >= 16 ? chunk / 4 : chunk;
   const size_t n = (size_t)npairs * n_per_pair;
   int rc = ensure(ctx, w, h, depth, chunk, n);
@@ -195,8 +202,11 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
     cudaStream_t cs = b ? r->compute2 : cs0;
     // ---- copy stream: frames of chunk k into staging buffer b (free once chunk k-2's pyramids are built)
     if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
-    rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride, c, xs);
-    if (!rc)
+    // independent pairs: the c from-frames, then the c to-frames; sequence: the c + seq_stride frames the chunk's pairs touch
+    const int nbuild = seq_stride ? c + seq_stride : 2 * c, to_first = seq_stride ? seq_stride : c;
+    rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride,
+                       seq_stride ? nbuild : c, xs);
+    if (!rc && !seq_stride)
       rc = upload_frames(ctx, r->d_frames[b] + (size_t)c * dense_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
                          row_stride, frame_stride, c, xs);
     if (rc) return rc;
@@ -204,8 +214,8 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
     // ---- pyramid stream: the pyramids of the chunk's frames into set k % 3 (free once chunk k-3 has been tracked)
     RCU(cudaStreamWaitEvent(ps, r->copied[b], 0));
     if (k >= 3) RCU(cudaStreamWaitEvent(ps, r->tracked[set], 0));
-    // one build for the 2c frames of the chunk: slots [0, c) the from-frames, [c, 2c) the to-frames
-    int nl = launch_pyr_build(r->pyr[set]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, 2 * c, ps);
+    // one build for the frames of the chunk: slots [0, c) the from-frames, [to_first, to_first + c) the to-frames
+    int nl = launch_pyr_build(r->pyr[set]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, nbuild, ps);
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "pyramid launch", (cudaError_t)(-nl));
     ctx->launches += nl;
     RCU(cudaEventRecord(r->consumed[b], ps));
@@ -214,7 +224,7 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
     RCU(cudaStreamWaitEvent(cs, r->built[set], 0));
     const size_t f0 = (size_t)p0 * n_per_pair;
     const int nf = c * n_per_pair;
-    TrackArgs ta{nf, n_per_pair, 0, c, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
+    TrackArgs ta{nf, n_per_pair, 0, to_first, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
                  thr, maxit, fb_max, r->d_back + 2 * f0, r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0, 2};
     nl = launch_track_hessian(r->pyr[set]->view, r->pyr[set]->view, ta, ctx->d_mask, ctx->d_counter + 16 * (1 + b),
                               ctx->num_sms, cs);
@@ -237,4 +247,27 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
   RCU(cudaStreamWaitEvent(cs, r->drained, 0));
   RCU(cudaStreamSynchronize(cs));
   return SFE_SUCCESS;
+}
+}  // namespace
+
+extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
+                                const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+                                const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
+                                int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                                uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+  return replay_run(ctx, w, h, depth, npairs, 0, from_bgr, to_bgr, row_stride, frame_stride, n_per_pair, from_xy, to_xy, levels,
+                    default_levels, thr, maxit, fb_max, back_xy, status_fwd, status_bwd, accepted, steps, chunk_pairs);
+}
+
+extern "C" int sfe_replay_sequence(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
+                                   const uint8_t* frames_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
+                                   const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
+                                   int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                                   uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+  if (!ctx) return SFE_ERR_INVALID;
+  if (pair_stride < 1 || nframes < 0) return rfail(ctx, SFE_ERR_INVALID, "bad sequence arguments", cudaSuccess);
+  if (nframes <= pair_stride) return SFE_SUCCESS;   // no pair
+  return replay_run(ctx, w, h, depth, nframes - pair_stride, pair_stride, frames_bgr, nullptr, row_stride, frame_stride, n_per_pair,
+                    from_xy, to_xy, levels, default_levels, thr, maxit, fb_max, back_xy, status_fwd, status_bwd, accepted, steps,
+                    chunk_pairs);
 }

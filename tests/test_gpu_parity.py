@@ -263,6 +263,29 @@ def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
     assert np.array_equal(out[0], oi) and np.array_equal(out[1], od) and np.array_equal(out[2], oo)
 
 
+@pytest.mark.parametrize("stride,chunk", [(2, 3), (1, 0), (2, 2), (3, 4)])
+def test_replay_sequence_equals_replay_pairs(fe, synth, stride, chunk):
+    """sfe_replay_sequence (one buffer of consecutive frames, pair i = (i, i + stride), every frame uploaded and built once
+    per chunk) gives bit for bit what sfe_replay_pairs gives on the pairs spelled out -- which is checked against the
+    oracle above -- incl. chunks shorter than the stride's halo and a ragged last chunk."""
+    H, W, nframes, npp = 240, 320, 13, 90
+    a, b = synth.make_pairs(71, nframes, H, W)
+    frames = a.numpy().copy()
+    frames[1::2] = b.numpy()[1::2]          # neighbouring frames related by the synthetic warp here and there
+    npairs = nframes - stride
+    pts = np.concatenate([_features(synth, npp, H, W, seed=90 + p) for p in range(npairs)])
+    lv = np.where(np.arange(npairs * npp) % 3 == 0, 2, 4).astype(np.int32)
+    ref = fe.replay_pairs(np.ascontiguousarray(frames[:npairs]), np.ascontiguousarray(frames[stride:]), pts, pts, depth=4,
+                          levels=lv, n_per_pair=npp, chunk_pairs=chunk)
+    got = fe.replay_sequence(frames, stride, pts, pts, depth=4, levels=lv, n_per_pair=npp, chunk_pairs=chunk)
+    for k in ("status_fwd", "status_bwd", "accepted", "steps"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert_bits_equal(got["to_xy"], ref["to_xy"], "to_xy")
+    assert_bits_equal(got["back_xy"], ref["back_xy"], "back_xy")
+    empty = fe.replay_sequence(frames[:stride], stride, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), depth=4, n_per_pair=npp)
+    assert empty["to_xy"].shape == (0, 2)
+
+
 def test_track_fb_empty_and_errors(fe, sfe, pair640):
     A, _ = pair640
     ga = fe.make_pyramid(A, 3)
