@@ -252,6 +252,22 @@ class ImageSourceFiles {
     return ReadFile(dir_ + "/" + b, &bytes) && DecodePng(bytes.data(), bytes.size(), img);
   }
 
+  // Consecutive frames first, first+1, ... into ONE contiguous buffer, for sfe_replay_sequence (pair i = (i, i + 2): the camera
+  // alternates every frame, main.cpp:503-519).  Stops at the first missing or differently sized frame; returns the number of
+  // frames loaded.
+  int LoadSequence(int first_id, int max_frames, std::vector<uint8_t>* frames_bgr, int* cols, int* rows) const {
+    frames_bgr->clear();
+    int n = 0;
+    BgrImage a;
+    for (; n < max_frames; ++n) {
+      if (!GetObservation(0, first_id + n, &a)) break;
+      if (n == 0) { *cols = a.cols; *rows = a.rows; }
+      if (a.cols != *cols || a.rows != *rows) break;
+      frames_bgr->insert(frames_bgr->end(), a.data.begin(), a.data.end());
+    }
+    return n;
+  }
+
   // Consecutive same-camera pairs (id, id + 2) for ids first, first+1, ... (main.cpp:503-519: the camera alternates
   // every frame) into the contiguous buffers sfe_replay_pairs takes.  Stops at the first missing frame, as the
   // reference's main loop does; returns the number of pairs loaded.

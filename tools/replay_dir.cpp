@@ -28,19 +28,21 @@ int main(int argc, char** argv) {
   sfe_ctx* ctx = nullptr;
   CHECK(sfe_create(0, &ctx));
   sfe::ImageSourceFiles src(argv[1]);
-  std::vector<uint8_t> from, to;
+  // the whole sequence in one buffer: pair p = (frame p, frame p + 2), every frame uploaded and its pyramid built once
+  std::vector<uint8_t> frames;
   int w = 0, h = 0;
-  const int npairs = src.LoadPairs(0, atoi(argv[2]), &from, &to, &w, &h);
-  if (npairs == 0) {
+  const int nframes = src.LoadSequence(0, atoi(argv[2]) + 2, &frames, &w, &h);
+  const int npairs = nframes - 2;
+  if (npairs <= 0) {
     fprintf(stderr, "no frame pairs under %s\n", argv[1]);
     return 1;
   }
   const int max_corners = 120;
   std::vector<float> corners((size_t)npairs * max_corners * 2, 0.f);
   std::vector<int32_t> ncorners(npairs, 0);
-  CHECK(sfe_good_features(ctx, from.data(), w, h, (size_t)3 * w, (size_t)3 * w * h, npairs, max_corners, 0.01, 20.0, corners.data(),
+  CHECK(sfe_good_features(ctx, frames.data(), w, h, (size_t)3 * w, (size_t)3 * w * h, npairs, max_corners, 0.01, 20.0, corners.data(),
                           ncorners.data(), nullptr));
-  // sfe_replay_pairs wants the same feature count per pair: pad short lists with the last corner (tracked twice, ignored below)
+  // the replay wants the same feature count per pair: pad short lists with the last corner (tracked twice, ignored below)
   const int n = npairs * max_corners;
   std::vector<float> from_xy(corners), to_xy, back(2 * (size_t)n);
   for (int p = 0; p < npairs; ++p)
@@ -51,8 +53,8 @@ int main(int argc, char** argv) {
   to_xy = from_xy;  // the seed is from_pt (uncertain map points, matcher.cpp:225)
   std::vector<int32_t> s1(n), s2(n);
   std::vector<uint8_t> acc(n);
-  CHECK(sfe_replay_pairs(ctx, w, h, 6, npairs, from.data(), to.data(), (size_t)3 * w, (size_t)3 * w * h, max_corners, from_xy.data(),
-                         to_xy.data(), nullptr, 3, 0.001f, 10, 0.3f, back.data(), s1.data(), s2.data(), acc.data(), nullptr, 0));
+  CHECK(sfe_replay_sequence(ctx, w, h, 6, nframes, 2, frames.data(), (size_t)3 * w, (size_t)3 * w * h, max_corners, from_xy.data(),
+                            to_xy.data(), nullptr, 3, 0.001f, 10, 0.3f, back.data(), s1.data(), s2.data(), acc.data(), nullptr, 0));
   FILE* out = argc > 3 ? fopen(argv[3], "w") : nullptr;
   for (int p = 0; p < npairs; ++p) {
     int m = 0;
