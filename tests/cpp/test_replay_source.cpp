@@ -30,5 +30,14 @@ int main(int argc, char** argv) {
   int w = 0, h = 0;
   const int n = src.LoadPairs(first, count, &a, &b, &w, &h);
   printf("pairs %d %d %d %zu %zu\n", n, w, h, a.size(), b.size());
+  // the same frames as one sequence buffer (sfe_replay_sequence): frame i of it is the from-frame of pair i
+  std::vector<uint8_t> seq;
+  int sw = 0, sh = 0;
+  const int nf = src.LoadSequence(first, count + 2, &seq, &sw, &sh);
+  const size_t fb = (size_t)3 * sw * sh;
+  bool same = nf == n + 2 && sw == w && sh == h && seq.size() == fb * nf;
+  for (int i = 0; same && i < n; ++i)
+    same = memcmp(&seq[i * fb], &a[i * fb], fb) == 0 && memcmp(&seq[(i + 2) * fb], &b[i * fb], fb) == 0;
+  printf("sequence %d %d\n", nf, same ? 1 : 0);
   return 0;
 }

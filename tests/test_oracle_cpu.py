@@ -232,6 +232,8 @@ def test_replay_source_reads_the_reference_png_format(tmp_path):
         assert np.array_equal(np.frombuffer(body, np.uint8).reshape(h, w, 3), ref), "frame %d" % i
     # frames 0..6 exist: pairs (0,2) (1,3) (2,4) (3,5) (4,6); (5,7) has no second frame
     assert r.stdout.split()[:4] == ["pairs", "5", "83", "60"]
+    # the same frames through LoadSequence (one buffer for sfe_replay_sequence): 7 frames, consistent with the pairs
+    assert r.stdout.split()[-3:] == ["sequence", "7", "1"]
 
 
 def test_hamming_edge_cases(po):
