@@ -89,18 +89,30 @@ static void gray_f32(const uint8_t* bgr, int w, int h, size_t stride, float* dst
   }
 }
 
-/* cv::GaussianBlur 5x5, BORDER_REFLECT_101, kernel (k2,k1,k0,k1,k2). dst may alias src. */
+/* cv::GaussianBlur 5x5, BORDER_REFLECT_101, kernel (k2,k1,k0,k1,k2). dst may alias src.
+ * OpenCV 4.13's AVX2 build evaluates the separable filter with FMAs in its vector bodies and with
+ * plain multiply/add in its scalar tails; which columns are "tail" is a pure function of the width
+ * (probed against cv2 column by column, tests/golden/make_golden.py re-runs the probe):
+ *   row filter     scalar only for the last column of an odd-width image
+ *   column filter  scalar for columns x >= (w/8)*8
+ * Both scalar forms are (k0*c + (m1+p1)*k1) + (m2+p2)*k2. */
 void orc_gauss5(const float* src, int w, int h, float k0, float k1, float k2, float* dst) {
   float* tmp = (float*)malloc(sizeof(float) * (size_t)w * h);
+  const int row_body = (w & 1) ? w - 1 : w, col_body = (w / 8) * 8;
   for (int y = 0; y < h; ++y) {
     const float* s = src + (size_t)y * w;
     float* t = tmp + (size_t)y * w;
     for (int x = 0; x < w; ++x) {
       float m2 = s[reflect101(x - 2, w)], m1 = s[reflect101(x - 1, w)], c = s[x];
       float p1 = s[reflect101(x + 1, w)], p2 = s[reflect101(x + 2, w)];
-      float r = (m1 + p1) * k1;
-      r = fmaf(k0, c, r);
-      r = fmaf(k2, m2 + p2, r);
+      float r;
+      if (x < row_body) {
+        r = (m1 + p1) * k1;
+        r = fmaf(k0, c, r);
+        r = fmaf(k2, m2 + p2, r);
+      } else {
+        r = (k0 * c + (m1 + p1) * k1) + (m2 + p2) * k2;
+      }
       t[x] = r;
     }
   }
@@ -111,12 +123,13 @@ void orc_gauss5(const float* src, int w, int h, float k0, float k1, float k2, fl
     const float* r3 = tmp + (size_t)reflect101(y + 1, h) * w;
     const float* r4 = tmp + (size_t)reflect101(y + 2, h) * w;
     float* d = dst + (size_t)y * w;
-    for (int x = 0; x < w; ++x) {
+    for (int x = 0; x < col_body; ++x) {
       float r = r2[x] * k0;
       r = fmaf(k1, r1[x] + r3[x], r);
       r = fmaf(k2, r0[x] + r4[x], r);
       d[x] = r;
     }
+    for (int x = col_body; x < w; ++x) d[x] = (k0 * r2[x] + (r1[x] + r3[x]) * k1) + (r0[x] + r4[x]) * k2;
   }
   free(tmp);
 }
@@ -143,17 +156,33 @@ void orc_gauss5_sigma(const float* src, int w, int h, double sigma, float* dst) 
   orc_gauss5(src, w, h, k0, k1, k2, dst);
 }
 
-/* cv::pyrDown, BORDER_REFLECT_101 (hessian.h:112). */
+/* cv::pyrDown, BORDER_REFLECT_101 (hessian.h:112).  As with GaussianBlur, OpenCV's vector bodies and
+ * scalar paths order the same sum differently, and the split is a function of the width alone (probed
+ * against cv2 4.13 column by column):
+ *   horizontal pass  border columns (0 and >= width0 = min((w-3)/2+1, dw)) go through the border table,
+ *                    columns 1..4*((width0-1)/4) through the 4-wide vector body, the rest of the middle
+ *                    through the scalar loop; table and scalar loop compute ((6c + 4(m1+p1)) + m2) + p2,
+ *                    the vector body ((m2+p2) + 4(m1+p1)) + 6c
+ *   vertical pass    columns x >= (dw/4)*4 are scalar: (((6 r2 + 4(r1+r3)) + r0) + r4) / 256,
+ *                    the vector body (4((r1+r3)+r2) + ((r0+r4)+(r2+r2))) / 256 */
+int orc_pyrdown_hbody(int w) { /* last column of the horizontal vector body (columns 1..n) */
+  int dw = (w + 1) / 2, width0 = (w - 3) / 2 + 1;
+  if (w < 3) width0 = 0;
+  if (width0 > dw) width0 = dw;
+  return width0 >= 1 ? ((width0 - 1) / 4) * 4 : 0;
+}
 void orc_pyrdown(const float* src, int w, int h, float* dst) {
   int dw = (w + 1) / 2, dh = (h + 1) / 2;
   float* tmp = (float*)malloc(sizeof(float) * (size_t)dw * h);
+  const int hbody = orc_pyrdown_hbody(w), vbody = (dw / 4) * 4;
   for (int y = 0; y < h; ++y) {
     const float* s = src + (size_t)y * w;
     float* t = tmp + (size_t)y * dw;
     for (int x = 0; x < dw; ++x) {
       float m2 = s[reflect101(2 * x - 2, w)], m1 = s[reflect101(2 * x - 1, w)], c = s[reflect101(2 * x, w)];
       float p1 = s[reflect101(2 * x + 1, w)], p2 = s[reflect101(2 * x + 2, w)];
-      t[x] = ((m2 + p2) + (m1 + p1) * 4.f) + c * 6.f;
+      if (x >= 1 && x <= hbody) t[x] = ((m2 + p2) + (m1 + p1) * 4.f) + c * 6.f;
+      else t[x] = ((c * 6.f + (m1 + p1) * 4.f) + m2) + p2;
     }
   }
   for (int y = 0; y < dh; ++y) {
@@ -163,8 +192,10 @@ void orc_pyrdown(const float* src, int w, int h, float* dst) {
     const float* r3 = tmp + (size_t)reflect101(2 * y + 1, h) * dw;
     const float* r4 = tmp + (size_t)reflect101(2 * y + 2, h) * dw;
     float* d = dst + (size_t)y * dw;
-    for (int x = 0; x < dw; ++x)
+    for (int x = 0; x < vbody; ++x)
       d[x] = (((r1[x] + r3[x]) + r2[x]) * 4.f + ((r0[x] + r4[x]) + (r2[x] + r2[x]))) * (1.f / 256.f);
+    for (int x = vbody; x < dw; ++x)
+      d[x] = (((r2[x] * 6.f + (r1[x] + r3[x]) * 4.f) + r0[x]) + r4[x]) * (1.f / 256.f);
   }
   free(tmp);
 }
@@ -179,7 +210,8 @@ void orc_scharr(const float* src, int w, int h, float* gx, float* gy) {
     for (int x = 0; x < w; ++x) {
       float m = s[reflect101(x - 1, w)], c = s[x], p = s[reflect101(x + 1, w)];
       tx[(size_t)y * w + x] = p - m;
-      ty[(size_t)y * w + x] = fmaf(k10, c, (m + p) * k3);
+      /* the row filter's scalar tail (last column of an odd-width image) fuses the other product */
+      ty[(size_t)y * w + x] = ((w & 1) && x == w - 1) ? fmaf(k3, m + p, c * k10) : fmaf(k10, c, (m + p) * k3);
     }
   }
   for (int y = 0; y < h; ++y) {

@@ -78,6 +78,7 @@ void orc_gray_u8(const uint8_t* bgr, int w, int h, size_t stride, uint8_t* gray)
 void orc_gauss5(const float* src, int w, int h, float sigma_id_k0, float k1, float k2, float* dst);
 void orc_gauss5_sigma(const float* src, int w, int h, double sigma, float* dst); /* sigma in {1.1,0.8,0.6} */
 void orc_pyrdown(const float* src, int w, int h, float* dst);           /* dst is ((w+1)/2,(h+1)/2) */
+int orc_pyrdown_hbody(int w); /* last column of cv::pyrDown's horizontal vector body for input width w */
 void orc_scharr(const float* src, int w, int h, float* gx, float* gy);  /* klt.h:105-106, scale 1/32 */
 void orc_rect_subpix(const float* img, int w, int h, int n, int m, float cx, float cy,
                      float* dst, int dst_pitch);                        /* cv::getRectSubPix 32f */

@@ -17,8 +17,9 @@ FLAVOR_HESSIAN, FLAVOR_KLT, FLAVOR_BRUTE = 0, 1, 2
 
 # brute.h:147-158 search schedules ({window, res} pairs)
 BRUTE_COARSE = np.array([3, 1, 1, 0.33333], dtype=np.float32)
-BRUTE_FINE = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025], dtype=np.float32)
-BRUTE_FINE_DEBUG = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025, 8, 0.01], dtype=np.float32)
+# BRUTE_FINE is the level-0 schedule as written (brute.h:154-158, incl. the (8, 0.01) pass); _FAST drops that pass
+BRUTE_FINE = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025, 8, 0.01], dtype=np.float32)
+BRUTE_FINE_FAST = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025], dtype=np.float32)
 
 
 class Counters(C.Structure):

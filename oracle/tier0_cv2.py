@@ -354,3 +354,253 @@ def hamming_knn2_cv2(q_bytes, t_bytes):
             idx[i, k] = m.trainIdx
             dist[i, k] = int(m.distance)
     return idx, dist
+
+
+# ------------------------------------------------------------------ P2 tier-0: KLTTracker (klt.h) on cv2 planes
+
+def klt_get_patch(level_planes, x, y):
+    """klt.h:59-96: three full 13x13 cv2.getRectSubPix calls (image, gradx, grady), no clipping."""
+    img, gx, gy = level_planes
+    c = (float(f32(x)), float(f32(y)))
+    data = cv2.getRectSubPix(img, (N, N), c)
+    m, q = patch_stats(data)
+    return data.ravel(), cv2.getRectSubPix(gx, (N, N), c).ravel(), cv2.getRectSubPix(gy, (N, N), c).ravel(), m, q
+
+
+def _lane_sums(terms, keep):
+    """Declared reduction of several masked fused accumulations at once: terms[j] is a list of (a, b) factor
+    arrays, accumulated per pixel as acc = fma(a, b, acc) where keep is set."""
+    out = []
+    for (a, b) in terms:
+        a = np.asarray(a, np.float32)
+        b = np.asarray(b, np.float32)
+
+        def acc_fn(acc, x, k, a=a, b=b):
+            kk = keep[k:k + len(x)]
+            return np.where(kk, fma(a[k:k + len(x)], b[k:k + len(x)], acc), acc)
+
+        out.append(lane_sum(a, acc_fn))
+    return out
+
+
+def klt_system(tmpl, cand):
+    """klt.h:286-343 for one (template patch, candidate patch) pair: the 24 numbers
+    A(4) B(4) C(4) RS(2) VW(2) U(4) e(2) d(2); tmpl / cand = (data, gradx, grady, mean, sumsq)."""
+    I, Igx, Igy, Im, Iq = tmpl
+    J0, Jgx, Jgy, Jm, Jq = cand
+    mask = _mask()
+    with np.errstate(all="ignore"):
+        alpha = f32(np.sqrt(f32(Iq) / f32(Jq)))             # :289
+        beta = f32(f32(Im) - alpha * f32(Jm))               # :290
+        keep = (J0 != 0) & (I != 0)                         # :303
+        Jv = fma(J0, alpha, beta)                           # :308
+        gJ0, gJ1 = (Jgx * alpha).astype(np.float32), (Jgy * alpha).astype(np.float32)  # :313
+        diff = ((I - Jv) * mask).astype(np.float32)         # :319
+        pairs = [(Igx * Igx, mask), (Igx * Igy, mask), (Igy * Igx, mask), (Igy * Igy, mask),          # A :316
+                 (Igx * gJ0, mask), (Igx * gJ1, mask), (Igy * gJ0, mask), (Igy * gJ1, mask),          # B :317
+                 (gJ0 * gJ0, mask), (gJ0 * gJ1, mask), (gJ1 * gJ0, mask), (gJ1 * gJ1, mask),          # C :318
+                 (diff, Igx), (diff, Igy), (diff, gJ0), (diff, gJ1)]                                  # RS, VW :320-321
+        s = _lane_sums(pairs, keep)
+        A, B, C, RS, VW = s[0:4], s[4:8], s[8:12], s[12:14], s[14:16]
+        lam = f32(.0001)                                    # :274
+        t00, t01, t10, t11 = B[0], B[2], B[1], B[3]         # B transposed (:326), Eigen's 2x2 closed-form inverse
+        det = f32(f32(t00 * t11) - f32(t10 * t01))
+        inv = f32(f32(1) / det)
+        D = [f32(t11 * inv), f32(-t01 * inv), f32(-t10 * inv), f32(t00 * inv)]
+        Al = [f32(A[0] + lam), A[1], A[2], f32(A[3] + lam)]
+        M = [f32(f32(Al[0] * D[0]) + f32(Al[1] * D[2])), f32(f32(Al[0] * D[1]) + f32(Al[1] * D[3])),
+             f32(f32(Al[2] * D[0]) + f32(Al[3] * D[2])), f32(f32(Al[2] * D[1]) + f32(Al[3] * D[3]))]
+        h = f32(0.5)
+        U = [f32(f32(f32(M[0] * C[0]) + f32(M[1] * C[2])) - f32(h * B[0])), f32(f32(f32(M[0] * C[1]) + f32(M[1] * C[3])) - f32(h * B[1])),
+             f32(f32(f32(M[2] * C[0]) + f32(M[3] * C[2])) - f32(h * B[2])), f32(f32(f32(M[2] * C[1]) + f32(M[3] * C[3])) - f32(h * B[3]))]  # :330
+        e = [f32(f32(f32(M[0] * VW[0]) + f32(M[1] * VW[1])) - f32(h * RS[0])),
+             f32(f32(f32(M[2] * VW[0]) + f32(M[3] * VW[1])) - f32(h * RS[1]))]                                                               # :331
+        u00, u01, u10, u11, e0, e1 = U[0], U[1], U[2], U[3], e[0], e[1]
+        if abs(u10) > abs(u00):                             # U.lu().solve(e) (:343): 2x2 partial-pivot LU
+            u00, u10, u01, u11, e0, e1 = u10, u00, u11, u01, e1, e0
+        l = f32(u10 / u00)
+        w11 = f32(u11 - f32(l * u01))
+        y1 = f32(e1 - f32(l * e0))
+        d1 = f32(y1 / w11)
+        d0 = f32(f32(e0 - f32(u01 * d1)) / u00)
+    return np.float32(list(A) + list(B) + list(C) + list(RS) + list(VW) + U + e + [d0, d1])
+
+
+def klt_brute_hessian(level_planes, patch, x, y):
+    """klt.h:181-204: forward differences, h = 0.01 (double)."""
+    h = 0.01
+    x, y = f32(x), f32(y)
+    x1, x2 = f32(float(x) + h), f32(float(x) + 2 * h)
+    y1, y2 = f32(float(y) + h), f32(float(y) + 2 * h)
+    pts = [(x, y), (x1, y), (x, y1), (x2, y), (x, y2), (x1, y1)]
+    s = [klt_sad(patch, cv2.getRectSubPix(level_planes[0], (N, N), (float(qx), float(qy)))) for (qx, qy) in pts]
+    return _fd(s, h, False)
+
+
+def klt_track(level_planes, tmpl, thr, maxit, x, y, trace):
+    """klt.h:258-401 as written: the symmetric-KLT step is computed (and recorded in `trace`), then replaced by
+    the finite-difference Newton step (klt.h:355-380)."""
+    x, y = f32(x), f32(y)
+    margin = f32(0.1)
+    h_, w_ = level_planes[0].shape
+    for _ in range(maxit):
+        if x < margin or y < margin or f32(x + margin) > f32(w_) or f32(y + margin) > f32(h_):
+            return OUT_OF_BOUNDS, x, y
+        sys24 = klt_system(tmpl, klt_get_patch(level_planes, x, y))
+        d6 = klt_brute_hessian(level_planes, tmpl[0], x, y)
+        if trace is not None:
+            trace.append((float(x), float(y), sys24, np.float32(d6)))
+        dx, dy = newton_step(d6)
+        x = f32(x + _clamp1(dx))
+        y = f32(y + _clamp1(dy))
+        if float(abs(dx)) < float(f32(thr)) / 10. and float(abs(dy)) < float(f32(thr)) / 10.:   # :392 (double compare)
+            break
+    return OK, x, y
+
+
+def klt_track_feature(tmpl_pyr, tx, ty, search_pyr, thr, maxit, x, y, traces=None):
+    """klt.h:249-256 + :403-424: all levels of the stack, coarse threshold x50."""
+    lvls = min(len(tmpl_pyr), len(search_pyr))
+    patches = []
+    qx, qy = f32(tx), f32(ty)
+    for i in range(lvls):
+        patches.append(klt_get_patch(tmpl_pyr[i], qx, qy))
+        qx, qy = f32(qx * f32(0.5)), f32(qy * f32(0.5))
+    scale = f32(1. / (1 << (lvls - 1)))
+    px, py = f32(f32(x) * scale), f32(f32(y) * scale)
+    for i in range(lvls - 1, -1, -1):
+        tr = None
+        if traces is not None:
+            tr = []
+            traces.append((i, tr))
+        st, px, py = klt_track(search_pyr[i], patches[i], f32(f32(thr) * f32(50)) if i > 0 else f32(thr), maxit, px, py, tr)
+        if st != OK:
+            return st, f32(x), f32(y)
+        if i > 0:
+            px, py = f32(px * f32(2)), f32(py * f32(2))
+    return OK, px, py
+
+
+def klt_track_fb(pfrom, pto, from_xy, thr=0.001, maxit=10, fb_max=0.3, traces=None):
+    """matcher.cpp:173-206 driven with the KLT tracker (seed = from_pt)."""
+    from_xy = np.asarray(from_xy, np.float32).reshape(-1, 2)
+    n = len(from_xy)
+    out = dict(to_xy=np.empty((n, 2), np.float32), back_xy=np.empty((n, 2), np.float32), status_fwd=np.empty(n, np.int32),
+               status_bwd=np.empty(n, np.int32), accepted=np.empty(n, np.uint8))
+    for i in range(n):
+        fx, fy = from_xy[i]
+        tr = [] if traces is not None else None
+        s1, tx, ty = klt_track_feature(pfrom, fx, fy, pto, thr, maxit, fx, fy, tr)
+        s2, bx, by = klt_track_feature(pto, tx, ty, pfrom, thr, maxit, fx, fy, None)
+        if traces is not None:
+            traces.append(tr)
+        ok = not (s1 or s2)
+        if ok:
+            ddx, ddy = f32(fx - bx), f32(fy - by)
+            if math.sqrt(float(ddx) * float(ddx) + float(ddy) * float(ddy)) > float(f32(fb_max)):
+                ok = False
+        out["to_xy"][i] = (tx, ty)
+        out["back_xy"][i] = (bx, by)
+        out["status_fwd"][i], out["status_bwd"][i], out["accepted"][i] = s1, s2, ok
+    return out
+
+
+# ------------------------------------------------------------------ P3 tier-0: BruteTracker (brute.h) on cv2 planes
+
+def _float_offsets(window, res):
+    """The offsets visited by `for (float x = -window; x <= window; x += res)` (brute.h:105-106), float32 counters."""
+    out = []
+    x, w, r = f32(-f32(window)), f32(window), f32(res)
+    while x <= w:
+        out.append(x)
+        x = f32(x + r)
+    return np.float32(out)
+
+
+def _batched_stats_and_sad(tmpl, tm, tq, cand):
+    """brute.h:34-57 statistics and brute.h:82-94 SAD for a batch of candidate patches [P,169], declared order,
+    vectorised over the batch."""
+    P = cand.shape[0]
+    pad = np.zeros((P, 192), np.float32)
+    pad[:, :LEN] = cand
+    lanes = pad.reshape(P, 6, 32)
+    s = np.zeros((P, 32), np.float32)
+    q = np.zeros((P, 32), np.float32)
+    for k in range(6):
+        n = 32 if k < 5 else LEN - 160
+        s[:, :n] = s[:, :n] + lanes[:, k, :n]
+        q[:, :n] = fma(lanes[:, k, :n], lanes[:, k, :n], q[:, :n])
+
+    def tree(v):
+        v = v.copy()
+        off = 16
+        while off:
+            v[:, :off] = v[:, :off] + v[:, off:2 * off]
+            off >>= 1
+        return v[:, 0]
+
+    mean = (tree(s) / f32(LEN)).astype(np.float32)
+    sumsq = (tree(q) / f32(LEN)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        alpha = np.sqrt(f32(tq) / sumsq).astype(np.float32)
+        beta = (f32(tm) - alpha * mean).astype(np.float32)
+        tp = np.zeros(192, np.float32)
+        tp[:LEN] = tmpl
+        tl = tp.reshape(6, 32)
+        acc = np.zeros((P, 32), np.float32)
+        for k in range(6):
+            n = 32 if k < 5 else LEN - 160
+            diff = (fma(-lanes[:, k, :n], alpha[:, None], tl[k, :n][None, :]) - beta[:, None]).astype(np.float32)
+            keep = (lanes[:, k, :n] != 0) & (tl[k, :n][None, :] != 0)
+            acc[:, :n] = np.where(keep, fma(diff, diff, acc[:, :n]), acc[:, :n])
+    return tree(acc)
+
+
+def brute_search_best(img, tmpl, tm, tq, window, res, px, py):
+    """brute.h:96-117: x outer, y inner, `if (sad > best) continue` -> the LAST minimum wins."""
+    offs = _float_offsets(window, res)
+    px, py = f32(px), f32(py)
+    best, bx, by = f32(1e6), px, py
+    for ox in offs:
+        cx = f32(px + ox)
+        cys = (py + offs).astype(np.float32)
+        cand = np.stack([cv2.getRectSubPix(img, (N, N), (float(cx), float(cy))).ravel() for cy in cys])
+        sads = _batched_stats_and_sad(tmpl, tm, tq, cand)
+        for j in range(len(cys)):   # sequential rule; NaN compares false, i.e. a NaN score is accepted like the reference
+            if sads[j] > best:
+                continue
+            bx, by, best = cx, cys[j], sads[j]
+    return best, bx, by, len(offs) * len(offs)
+
+
+BRUTE_COARSE = [(3, 1), (1, 0.33333)]                                         # brute.h:147-148
+BRUTE_FINE = [(3, 1), (1, 0.3333), (0.4, 0.1), (0.2, 0.025), (8, 0.01)]       # brute.h:154-158, as written
+
+
+def brute_track_feature(tmpl_pyr, tx, ty, search_pyr, x, y, coarse=BRUTE_COARSE, fine=BRUTE_FINE, trace=None):
+    """brute.h:129-164 with the schedule as written (incl. the (8, 0.01) pass)."""
+    lvls = min(len(tmpl_pyr), len(search_pyr))
+    margin = f32(13)
+    h0, w0 = search_pyr[0].shape
+    x, y = f32(x), f32(y)
+    if x < margin or y < margin or f32(x + margin) > f32(w0) or f32(y + margin) > f32(h0):
+        return OUT_OF_BOUNDS, x, y, f32(0)
+    patches = []
+    qx, qy = f32(tx), f32(ty)
+    for i in range(lvls):
+        patches.append(full_patch(tmpl_pyr[i], qx, qy))
+        qx, qy = f32(qx * f32(0.5)), f32(qy * f32(0.5))
+    scale = f32(1. / (1 << (lvls - 1)))
+    px, py = f32(x * scale), f32(y * scale)
+    sad = f32(0)
+    for i in range(lvls - 1, -1, -1):
+        d, m, q = patches[i]
+        for (win, res) in (coarse if i > 0 else fine):
+            sad, px, py, npos = brute_search_best(search_pyr[i], d.ravel(), m, q, win, res, px, py)
+            if trace is not None:
+                trace.append((i, float(win), float(res), float(px), float(py), float(sad), npos))
+        if sad > 100:
+            return OUT_OF_BOUNDS, x, y, sad
+        if i > 0:
+            px, py = f32(px * f32(2)), f32(py * f32(2))
+    return OK, px, py, sad

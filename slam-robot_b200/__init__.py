@@ -22,9 +22,13 @@ OK, SMALL_DET, OUT_OF_BOUNDS = 0, 1, 2          # hessian.h:48-52
 HESSIAN, KLT, BRUTE = 0, 1, 2                   # pyramid flavours
 MAX_LEVELS = 12
 
-# brute.h:147-148 / :154-157 search schedules ({window,res} pairs); :158 is the debug pass
+# brute.h:147-148 / :154-158 search schedules ({window,res} pairs), AS WRITTEN: the last level-0 pass (8, 0.01)
+# -- 1600 x 1600 positions per feature under the reference's float loop counters -- is live code: it sets the final
+# position and the `sad` of the `sad > 100` gate (brute.h:158-159).  BRUTE_FINE_FAST drops it (an explicitly named
+# variant, 2.5 M fewer positions per feature; NOT what BruteTracker::TrackFeature computes).
 BRUTE_COARSE = np.array([3, 1, 1, 0.33333], dtype=np.float32)
-BRUTE_FINE = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025], dtype=np.float32)
+BRUTE_FINE = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025, 8, 0.01], dtype=np.float32)
+BRUTE_FINE_FAST = np.array([3, 1, 1, 0.3333, 0.4, 0.1, 0.2, 0.025], dtype=np.float32)
 
 EXPORTS = [
     "sfe_create", "sfe_destroy", "sfe_last_error", "sfe_set_stream", "sfe_sync", "sfe_get_mask", "sfe_host_alloc",

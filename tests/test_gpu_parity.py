@@ -334,8 +334,8 @@ def test_brute_track_bit_exact(fe, po, sfe, synth):
     pts[:4] = [[5, 100], [100, 8], [W - 6, 100], [100, H - 5]]  # inside the margin-13 band -> OUT_OF_BOUNDS
     ga, gb = fe.make_pyramid(A, 3, sfe.BRUTE), fe.make_pyramid(B, 3, sfe.BRUTE)
     oa, ob = po.Pyramid(A, 3, po.FLAVOR_BRUTE), po.Pyramid(B, 3, po.FLAVOR_BRUTE)
-    g = fe.brute_track(ga, gb, pts, pts)
-    o = po.brute_track(oa, ob, pts, pts)
+    g = fe.brute_track(ga, gb, pts, pts, fine=sfe.BRUTE_FINE_FAST)
+    o = po.brute_track(oa, ob, pts, pts, fine=po.BRUTE_FINE_FAST)
     assert np.array_equal(g["status"], o["status"])
     assert_bits_equal(g["to_xy"], o["to_xy"], "brute to_xy")
     assert_bits_equal(g["best_sad"], o["best_sad"], "brute best_sad")
@@ -343,6 +343,27 @@ def test_brute_track_bit_exact(fe, po, sfe, synth):
     truth = synth.true_motion(pts, H, W, 0.004, (1.7, -2.3))
     ok = g["status"] == 0
     assert ok.sum() >= n - 8 and np.median(np.linalg.norm(g["to_xy"] - truth, axis=1)[ok]) < 0.15
+
+
+def test_brute_track_reference_schedule_bit_exact(fe, po, sfe, synth):
+    """BruteTracker::TrackFeature AS WRITTEN (brute.h:129-164): the default schedule includes the last level-0 pass
+    SearchBest(stack[0], patches[0], 8, 0.01, &p) (brute.h:158), 1600 x 1600 positions per feature, which decides the
+    returned position and the sad of the `sad > 100` gate.  A handful of features, bit-exact against the oracle, which
+    is itself pinned to a tier-0 (cv2.getRectSubPix) run of the same schedule by tests/golden/brute_tracks.npz."""
+    H, W = 97, 131
+    A, B = synth.make_pairs(42, 1, H, W)
+    A, B = A[0].numpy(), B[0].numpy()
+    pts = synth.make_features(12, 6, H, W, margin=20)
+    pts[5] = [W - 14.5, 30.25]  # the 8 px window reaches past the right border: the tile holds replicated columns
+    assert len(sfe.BRUTE_FINE) == 10 and tuple(sfe.BRUTE_FINE[-2:]) == (8.0, np.float32(0.01))
+    ga, gb = fe.make_pyramid(A, 3, sfe.BRUTE), fe.make_pyramid(B, 3, sfe.BRUTE)
+    oa, ob = po.Pyramid(A, 3, po.FLAVOR_BRUTE), po.Pyramid(B, 3, po.FLAVOR_BRUTE)
+    g = fe.brute_track(ga, gb, pts, pts)          # defaults = the reference's schedule
+    o = po.brute_track(oa, ob, pts, pts)
+    assert np.array_equal(g["status"], o["status"])
+    assert_bits_equal(g["to_xy"], o["to_xy"], "brute to_xy (reference schedule)")
+    assert_bits_equal(g["best_sad"], o["best_sad"], "brute best_sad (reference schedule)")
+    assert g["positions"] == o["positions"] and g["positions"] >= 6 * 1600 * 1600
 
 
 @pytest.mark.parametrize("nq,nt,batch", [(2000, 2000, 1), (777, 1301, 3), (1, 1, 1), (5, 0, 1), (300, 1, 2), (4096, 70000, 1)])

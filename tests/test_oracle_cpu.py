@@ -34,17 +34,13 @@ def test_mask_properties(po):
 
 
 def test_pyramid_hessian_vs_cv2_golden(po):
+    """hessian.h:95-126: every level bit-identical to the cv2-built pyramid, scalar-tail columns included (131 = 16*8+3
+    columns at level 0, 66 / 33 / 17 above: every tail rule of oracle.h is exercised)."""
     g = gold("pyramid.npz")
     for key, frame in (("hes_a", g["A"]), ("hes_b", g["B"])):
         p = po.Pyramid(frame, 4, po.FLAVOR_HESSIAN)
         for l in range(4):
-            ref, got = g["%s%d" % (key, l)], p.plane(l)
-            assert got.shape == ref.shape
-            assert ulps(got, ref).max() <= 2, "level %d" % l
-            if l == 0:  # level 0: exact wherever OpenCV's 8-wide SIMD body ran
-                main = ref.shape[1] & ~7
-                assert_bits_equal(got[:, :main], ref[:, :main], "L0 SIMD columns")
-            assert (got == ref).mean() > (0.9 if l < 2 else 0.7)  # tail columns weigh more on tiny levels
+            assert_bits_equal(p.plane(l), g["%s%d" % (key, l)], "%s level %d" % (key, l))
 
 
 def test_pyramid_klt_and_brute_vs_cv2_golden(po):
@@ -52,14 +48,37 @@ def test_pyramid_klt_and_brute_vs_cv2_golden(po):
     pk = po.Pyramid(g["A"], 3, po.FLAVOR_KLT)
     for l in range(3):
         for k in range(3):
-            ref, got = g["klt_a%d_%d" % (l, k)], pk.plane(l, k)
-            d = np.abs(got - ref).max()
-            assert d <= 2.5e-7, (l, k, d)  # <= 2 ulp of values in [-1, 1]
-            assert (got == ref).mean() > (0.9 if l < 2 else 0.7)
+            assert_bits_equal(pk.plane(l, k), g["klt_a%d_%d" % (l, k)], "klt level %d plane %d" % (l, k))
     pb = po.Pyramid(g["A"], 3, po.FLAVOR_BRUTE)
-    assert_bits_equal(pb.plane(0), g["bru_a0"], "brute L0 (gray/255)")
-    for l in (1, 2):
-        assert ulps(pb.plane(l), g["bru_a%d" % l]).max() <= 2
+    for l in range(3):
+        assert_bits_equal(pb.plane(l), g["bru_a%d" % l], "brute level %d" % l)
+
+
+def sha(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+@pytest.mark.parametrize("name", ["vga", "hd"])
+def test_pyramid_measured_shapes_vs_cv2_digests(po, synth, name):
+    """The shapes bench.py measures (C2: 640x480, C3: 1920x1080 / 8 levels): every plane of the oracle's pyramid has
+    the SHA-256 of the cv2-built one (tests/golden/make_golden.py; the planes are too large to commit), and the
+    border / scalar-tail columns are compared in full so that a mismatch names a column."""
+    g = gold("pyramid640.npz")
+    seed, h, w, depth = (int(v) for v in g[name + "_seed"])
+    fr = synth.make_frames(seed, 1, h, w).numpy()[0]
+    assert int(po.gray_u8(fr).astype(np.int64).sum()) == int(g[name + "_gray_sum"]), "synthetic frame generator changed"
+    p = po.Pyramid(fr, depth, po.FLAVOR_HESSIAN)
+    for l in range(depth):
+        got = p.plane(l)
+        assert_bits_equal(np.concatenate([got[:, :1], got[:, -8:]], axis=1), g["%s_hes%d_tail" % (name, l)], "level %d tails" % l)
+        assert np.array_equal(sha(got), g["%s_hes%d_sha" % (name, l)]), "level %d differs from cv2" % l
+    if name == "vga":
+        pk, pb = po.Pyramid(fr, 3, po.FLAVOR_KLT), po.Pyramid(fr, 3, po.FLAVOR_BRUTE)
+        for l in range(3):
+            for k in range(3):
+                assert np.array_equal(sha(pk.plane(l, k)), g["vga_klt%d_%d_sha" % (l, k)]), (l, k)
+            assert np.array_equal(sha(pb.plane(l)), g["vga_bru%d_sha" % l]), l
 
 
 def golden_pyr(po, key, depth):
@@ -102,18 +121,58 @@ def test_tracks_bit_exact_on_cv2_planes(po, levels):
     assert r["accepted"].sum() >= 60
 
 
-def test_tracks_own_pyramid_close_to_cv2_pipeline(po):
-    """Whole pipeline (oracle pyramid, <=2 ulp from cv2's in SIMD-tail columns) against the whole cv2
-    pipeline: identical flags / <=1e-3 px except for noise-sensitive features, which
-    must stay rare and are reported, not hidden."""
+def test_tracks_own_pyramid_equal_cv2_pipeline(po):
+    """Whole pipeline (oracle pyramid + oracle tracker) against the whole cv2 pipeline (cv2 pyramid + tier-0 tracker):
+    0 of 80 features differ -- positions bit for bit, statuses and accept flags identical (north_star asks for 1e-3 px
+    and identical lost-track flags)."""
     g, gp = gold("tracks.npz"), gold("pyramid.npz")
     pa, pb = po.Pyramid(gp["A"], 4), po.Pyramid(gp["B"], 4)
-    r = po.hes_track_fb(pa, pb, g["xy"], g["xy"], 3)
-    same_flag = r["accepted"] == g["l3_accepted"]
-    close = np.linalg.norm(r["to_xy"] - g["l3_to_xy"], axis=1) <= 1e-3
-    sensitive = np.flatnonzero(~(same_flag & close))
-    print("noise-sensitive features:", sensitive.tolist())
-    assert len(sensitive) <= 0.05 * len(same_flag)
+    for levels in (3, 4):
+        r = po.hes_track_fb(pa, pb, g["xy"], g["xy"], levels)
+        pre = "l%d_" % levels
+        for k in ("status_fwd", "status_bwd", "accepted"):
+            assert np.array_equal(r[k], g[pre + k]), k
+        assert_bits_equal(r["to_xy"], g[pre + "to_xy"], "to_xy")
+        assert_bits_equal(r["back_xy"], g[pre + "back_xy"], "back_xy")
+
+
+def test_klt_systems_and_tracks_vs_tier0_golden(po):
+    """klt.h on the real cv2 planes (tier-0) -- every Newton iteration's point, its 24 numbers
+    A,B,C,RS,VW,U,e,d (klt.h:286-343) and six finite differences, and the forward/backward results -- reproduced bit
+    for bit by the C oracle on ITS OWN pyramids (which equal cv2's, test above)."""
+    g, gp = gold("klt_tracks.npz"), gold("pyramid.npz")
+    pa, pb = po.Pyramid(gp["A"], 3, po.FLAVOR_KLT), po.Pyramid(gp["B"], 3, po.FLAVOR_KLT)
+    pts = g["xy"]
+    r = po.klt_track_fb(pa, pb, pts, pts)
+    for k in ("status_fwd", "status_bwd", "accepted"):
+        assert np.array_equal(r[k], g[k]), k
+    assert_bits_equal(r["to_xy"], g["to_xy"], "klt to_xy")
+    assert_bits_equal(r["back_xy"], g["back_xy"], "klt back_xy")
+    assert len(g["it_feature"]) > 100
+    for j in range(len(g["it_feature"])):
+        i, lvl = int(g["it_feature"][j]), int(g["it_level"][j])
+        sc = np.float32(1. / (1 << lvl))
+        got = po.klt_system(pa, np.float32(pts[i, 0] * sc), np.float32(pts[i, 1] * sc), pb, lvl, g["it_xy"][j, 0], g["it_xy"][j, 1])
+        assert_bits_equal(got, g["it_sys24"][j], "klt system of iteration %d (feature %d level %d)" % (j, i, lvl))
+
+
+def test_brute_search_best_vs_tier0_golden(po):
+    """brute.h SearchBest arg-mins from tier-0 (cv2.getRectSubPix): the four cheap passes on 8
+    features, and the schedule AS WRITTEN incl. (8, 0.01) = 1600 x 1600 positions (brute.h:158) on 2 features."""
+    g, gp = gold("brute_tracks.npz"), gold("pyramid.npz")
+    pa, pb = po.Pyramid(gp["A"], 3, po.FLAVOR_BRUTE), po.Pyramid(gp["B"], 3, po.FLAVOR_BRUTE)
+    pts = g["xy"]
+    r = po.brute_track(pa, pb, pts, pts, fine=po.BRUTE_FINE_FAST)
+    assert np.array_equal(r["status"], g["fast_status"])
+    assert_bits_equal(r["to_xy"], g["fast_final"][:, :2], "fast schedule positions")
+    assert_bits_equal(r["best_sad"], g["fast_final"][:, 2], "fast schedule scores")
+    assert r["positions"] == 8 * int(g["fast_positions_per_feature"])
+    # every pass on its own: restart the search from the previous pass's arg-min (level-0 passes of feature 0)
+    r2 = po.brute_track(pa, pb, pts[:2], pts[:2])   # defaults = the reference's schedule
+    assert np.array_equal(r2["status"], g["ref_status"])
+    assert_bits_equal(r2["to_xy"], g["ref_final"][:, :2], "reference schedule positions")
+    assert_bits_equal(r2["best_sad"], g["ref_final"][:, 2], "reference schedule scores")
+    assert r2["positions"] == 2 * int(g["ref_positions_per_feature"]) == 2 * 2560631
 
 
 def test_hamming_vs_cv2_bfmatcher_golden(po):
@@ -291,7 +350,7 @@ def test_klt_and_brute_oracle_properties(po, synth):
     assert np.allclose(s[0:4], s[4:8], rtol=1e-6) and np.allclose(s[0:4], s[8:12], rtol=1e-6)
     assert np.abs(s[12:16]).max() < 1e-6 and np.abs(s[22:24]).max() < 1e-4
     ba, bb = po.Pyramid(A, 3, po.FLAVOR_BRUTE), po.Pyramid(B, 3, po.FLAVOR_BRUTE)
-    rb = po.brute_track(ba, bb, pts, pts)
+    rb = po.brute_track(ba, bb, pts, pts, fine=po.BRUTE_FINE_FAST)
     okb = rb["status"] == 0
     assert okb.sum() >= 36 and np.median(np.linalg.norm(rb["to_xy"] - truth, axis=1)[okb]) < 0.2
     # float loop counters (brute.h:105-106): `x += res` accumulates rounding, e.g. (0.2, 0.025) visits 16
@@ -303,8 +362,8 @@ def test_klt_and_brute_oracle_properties(po, synth):
             x = np.float32(x + np.float32(res))
         return n * n
     coarse = sum(count(w, r) for w, r in po.BRUTE_COARSE.reshape(-1, 2))
-    fine = sum(count(w, r) for w, r in po.BRUTE_FINE.reshape(-1, 2))
-    assert count(0.2, 0.025) == 256
+    fine = sum(count(w, r) for w, r in po.BRUTE_FINE_FAST.reshape(-1, 2))
+    assert count(0.2, 0.025) == 256 and count(8, 0.01) == 1600 * 1600  # not 1601^2
     assert rb["positions"] == okb.sum() * (2 * coarse + fine)
 
 
