@@ -1,8 +1,18 @@
 // pyr_math.cuh -- the per-pixel arithmetic of MakePyramid shared by the pyramid kernels.
 // Operation order and FMA placement are those of oracle/oracle.c (pinned bit-for-bit against OpenCV 4.13):
 // cv::GaussianBlur 5x5 (separable, rows then columns) and cv::pyrDown ([1 4 6 4 1]/16 per axis, /256 once).
-// Every formula is symmetric under reversing its five taps, which is what lets the streaming kernels
-// extend an image by reflection instead of special-casing BORDER_REFLECT_101.
+//
+// OpenCV evaluates each filter with one operation order in its vector bodies and another in its scalar
+// paths (row tails, border tables), and which column takes which path is a function of the level's width
+// alone (oracle.c orc_gauss5 / orc_pyrdown state the rules, probed against cv2 column by column).  The
+// *_tail predicates below are those rules; the *_sc functions are the scalar-path forms.  Results are
+// bit-identical to cv2 in every column, not only where the vector body ran.
+//
+// The vector-body forms and the blur's scalar form are symmetric under reversing their five taps, which is
+// what lets the streaming kernels extend an image by reflection instead of special-casing
+// BORDER_REFLECT_101; the pyrDown scalar forms are NOT symmetric (((6c + 4(m1+p1)) + m2) + p2), so the
+// streaming kernels only take widths for which the vertical pyrDown pass has no scalar columns (w % 8 == 0)
+// and apply the horizontal scalar form at real column positions only.
 #pragma once
 #include "sfe_common.cuh"
 
@@ -46,5 +56,30 @@ __device__ __forceinline__ float pd_h(float m2, float m1, float c, float p1, flo
 __device__ __forceinline__ float pd_v(float r0, float r1, float r2, float r3, float r4) {
   return (((r1 + r3) + r2) * 4.f + ((r0 + r4) + (r2 + r2))) * (1.f / 256.f);
 }
+
+// ---- OpenCV's scalar-path forms (no FMA; -fmad=false keeps them unfused) and the columns that take them
+__device__ __forceinline__ float blur_sc(float m2, float m1, float c, float p1, float p2, Taps t) {  // rows and columns
+  return (t.k0 * c + (m1 + p1) * t.k1) + (m2 + p2) * t.k2;
+}
+__device__ __forceinline__ float pd_h_sc(float m2, float m1, float c, float p1, float p2) {
+  return ((c * 6.f + (m1 + p1) * 4.f) + m2) + p2;
+}
+__device__ __forceinline__ float pd_v_sc(float r0, float r1, float r2, float r3, float r4) {
+  return (((r2 * 6.f + (r1 + r3) * 4.f) + r0) + r4) * (1.f / 256.f);
+}
+// GaussianBlur of a w-wide level: the row filter is scalar in the last column of an odd width, the column filter
+// in columns >= (w/8)*8
+__host__ __device__ inline bool blur_row_tail(int x, int w) { return (w & 1) && x == w - 1; }
+__host__ __device__ inline bool blur_col_tail(int x, int w) { return x >= (w & ~7); }
+// pyrDown of a w-wide level into dw = (w+1)/2 columns: the horizontal pass runs its vector body on output columns
+// 1..pd_hbody(w), the border table / scalar loop elsewhere; the vertical pass is scalar in columns >= (dw/4)*4
+__host__ __device__ inline int pd_hbody(int w) {
+  const int dw = (w + 1) / 2;
+  int width0 = w < 3 ? 0 : (w - 3) / 2 + 1;
+  width0 = width0 < dw ? width0 : dw;
+  return width0 >= 1 ? ((width0 - 1) / 4) * 4 : 0;
+}
+__host__ __device__ inline bool pd_h_tail(int x1, int hbody) { return x1 < 1 || x1 > hbody; }
+__host__ __device__ inline bool pd_v_tail(int x1, int dw) { return x1 >= (dw & ~3); }
 
 }  // namespace

@@ -17,7 +17,11 @@
 // (the mirror axes of the two grids differ), so there the last in-image lane takes its out-of-image
 // neighbours from the mirrored pixels it already holds, and the last two level-1 rows take their
 // out-of-image pyrDown rows from the mirrored rows still in the window.
-// The arithmetic per pixel is pyr_math.cuh's, i.e. bit-identical to the tiled kernels and the oracle.
+// The arithmetic per pixel is pyr_math.cuh's, i.e. bit-identical to the tiled kernels and the oracle -- including
+// OpenCV's scalar-path operation orders in the columns that take them: with widths that are multiples of 8 (the
+// only ones these kernels accept) those are the horizontal pyrDown pass in output column 0 and in the last
+// columns behind its vector body (pd_h_tail), and the level-1 column blur when w/2 is not a multiple of 8
+// (blur_col_tail).  Only the warps that own such columns execute the second form (a warp-uniform branch).
 #include <stdlib.h>
 
 #include "pyr_math.cuh"
@@ -44,6 +48,7 @@ struct StreamArgs {
   int first;               // first frame slot in the pyramid batch
   int strips, bands, band_rows, nunits;
   float scale;             // DOWN_ONLY: factor applied to the pyrDown result (klt.h:123-124 doubles the gradients)
+  int hbody;               // pd_hbody(w): last output column of cv::pyrDown's horizontal vector body
 };
 
 __device__ __forceinline__ float gray_px(uint32_t p) {
@@ -102,6 +107,11 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
   const bool inimg = g >= 0 && g < a.w;                        // w % 4 == 0: the group is all in or all out
   const bool ledge = g == 0, redge = g == a.w - 4;
   const bool useful = inimg && lane >= 2 && lane <= 29;
+  // OpenCV's scalar-path columns (pyr_math.cuh): this lane's two pyrDown columns g/2, g/2+1, and the level-1 column blur
+  const bool tail_x = inimg && pd_h_tail(g >> 1, a.hbody), tail_y = inimg && pd_h_tail((g >> 1) + 1, a.hbody);
+  const bool warp_tail = __any_sync(SFE_FULL, tail_x || tail_y);
+  const bool ctail = inimg && blur_col_tail(g >> 1, a.w1);
+  const bool warp_ctail = __any_sync(SFE_FULL, ctail);
   const int r0 = band * a.band_rows;                           // band of input rows [r0, r1); band_rows is even
   const int r1 = min(r0 + a.band_rows, 2 * a.h1);
   const int q_hi = min(r1, a.h), j_lo = r0 >> 1, j_hi = min(r1 >> 1, a.h1);
@@ -189,7 +199,12 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         float rx = __shfl_down_sync(SFE_FULL, row.x, 1);
         if (ledge) { lz = row.z; lw = row.y; }
         if (redge) rx = row.z;
-        phw[u % 5] = make_float2(pd_h(lz, lw, row.x, row.y, row.z), pd_h(row.x, row.y, row.z, row.w, rx));
+        float2 ph = make_float2(pd_h(lz, lw, row.x, row.y, row.z), pd_h(row.x, row.y, row.z, row.w, rx));
+        if (warp_tail) {
+          if (tail_x) ph.x = pd_h_sc(lz, lw, row.x, row.y, row.z);
+          if (tail_y) ph.y = pd_h_sc(row.x, row.y, row.z, row.w, rx);
+        }
+        phw[u % 5] = ph;
       }
       if (u % 2 == 0) {
         // pyrDown columns: row i = (q-2)/2 from input rows q-4..q
@@ -215,8 +230,11 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
         bhw[v] = bh;
         const float2 &b0 = bhw[(v + 1) % 5], &b1 = bhw[(v + 2) % 5], &b2 = bhw[(v + 3) % 5], &b3 = bhw[(v + 4) % 5], &b4 = bhw[v];
         const int j = i - 2;
-        if (useful && j >= j_lo && j < j_hi)
-          *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) = blur_col2(b0, b1, b2, b3, b4, k1);
+        float2 o = blur_col2(b0, b1, b2, b3, b4, k1);
+        if (warp_ctail) {
+          if (ctail) o = make_float2(blur_sc(b0.x, b1.x, b2.x, b3.x, b4.x, k1), blur_sc(b0.y, b1.y, b2.y, b3.y, b4.y, k1));
+        }
+        if (useful && j >= j_lo && j < j_hi) *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) = o;
       }
     }
   }
@@ -303,6 +321,10 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   unsigned char* ring = row_smem + sizeof(Bufs) + (size_t)warp * RING * 32 * 12;
 
   const int g = 4 * L;
+  // OpenCV's scalar-path columns of the horizontal pyrDown pass (pyr_math.cuh): column 0 and the last few, i.e. lanes
+  // of the first and the last warp only (w1 = 64 NW is a multiple of 8: the level-1 column blur has no tail)
+  const bool tail_x = pd_h_tail(2 * L, a.hbody), tail_y = pd_h_tail(2 * L + 1, a.hbody);
+  const bool warp_tail = __any_sync(SFE_FULL, tail_x || tail_y);
   const int r0 = band * a.band_rows;
   const int r1 = min(r0 + a.band_rows, 2 * a.h1);
   const int q_hi = min(r1, a.h), j_lo = r0 >> 1, j_hi = min(r1 >> 1, a.h1);
@@ -393,7 +415,12 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
       {
         const float2 l = lds2(lb + LZW + prev);
         const float r = lds1(lb + LXY + prev + 8);
-        phw[u % 5] = make_float2(pd_h(l.x, l.y, rowp.x, rowp.y, rowp.z), pd_h(rowp.x, rowp.y, rowp.z, rowp.w, r));
+        float2 ph = make_float2(pd_h(l.x, l.y, rowp.x, rowp.y, rowp.z), pd_h(rowp.x, rowp.y, rowp.z, rowp.w, r));
+        if (warp_tail) {
+          if (tail_x) ph.x = pd_h_sc(l.x, l.y, rowp.x, rowp.y, rowp.z);
+          if (tail_y) ph.y = pd_h_sc(rowp.x, rowp.y, rowp.z, rowp.w, r);
+        }
+        phw[u % 5] = ph;
       }
       if (u % 2 == 0) {
         // pyrDown columns: row i = (qd-2)/2 from level-0 rows qd-4..qd, published for the next tick
@@ -499,13 +526,15 @@ void launch_row(StreamArgs& a, int count, cudaStream_t s) {
 // or 0 when the geometry does not qualify (the caller falls back to the tiled kernels for all levels).
 int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first,
                               int count, cudaStream_t s, int* launches) {
-  auto ok_level = [](int w, int h) { return w % 4 == 0 && w >= 16 && h >= 16; };
+  // w % 8 == 0: cv::pyrDown's vertical pass then has no scalar columns (pyr_math.cuh); other widths take the tiled kernels
+  auto ok_level = [](int w, int h) { return w % 8 == 0 && w >= 16 && h >= 16; };
   if (v.depth < 2 || !ok_level(v.w[0], v.h[0]) || ((uintptr_t)bgr & 3) || row_stride % 4 || frame_stride % 4) return 0;
   int built = 0;
   for (int l = 1; l < v.depth; ++l) {
     if (!ok_level(v.w[l - 1], v.h[l - 1])) break;
     StreamArgs a{};
     a.w = v.w[l - 1]; a.h = v.h[l - 1]; a.w1 = v.w[l]; a.h1 = v.h[l];
+    a.hbody = pd_hbody(a.w);
     a.first = first;
     a.strips = (a.w + STRIP_USEFUL - 1) / STRIP_USEFUL;
     a.out1 = v.base[0][l]; a.out1_fs = v.frame_stride[l]; a.out1_pitch = v.pitch[l];
@@ -537,9 +566,10 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
 // then uses the tiled kernel).
 int launch_pyr_stream_down(const PyrView& v, int plane, int l, int first, int count, int blur_id, float scale, cudaStream_t s) {
   static const bool tiled_only = getenv("SFE_PYR_TILED") != nullptr;
-  if (tiled_only || l < 1 || v.w[l - 1] % 4 != 0 || v.w[l - 1] < 16 || v.h[l - 1] < 16 || blur_id == 0 || blur_id > 2) return 0;
+  if (tiled_only || l < 1 || v.w[l - 1] % 8 != 0 || v.w[l - 1] < 16 || v.h[l - 1] < 16 || blur_id == 0 || blur_id > 2) return 0;
   StreamArgs a{};
   a.w = v.w[l - 1]; a.h = v.h[l - 1]; a.w1 = v.w[l]; a.h1 = v.h[l];
+  a.hbody = pd_hbody(a.w);
   a.first = first;
   a.strips = (a.w + STRIP_USEFUL - 1) / STRIP_USEFUL;
   a.in = v.base[plane][l - 1]; a.in_fs = v.frame_stride[l - 1]; a.in_pitch = v.pitch[l - 1];

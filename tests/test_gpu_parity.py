@@ -228,6 +228,53 @@ def test_track_fb_batched_pairs(fe, po, synth):
         assert_bits_equal(g["back_xy"][sl], o["back_xy"], "pair %d back_xy" % p)
 
 
+def test_config2_measured_shape_bit_exact(fe, po, sfe, synth):
+    """BASELINE config 2 exactly as bench.py runs it: 640x480 pairs, 2000 features per pair, a 4-level pyramid, several
+    pairs per step in ONE pyramid batch of 2B slots (slots [0,B) = first frames, [B,2B) = second frames, built by one
+    sfe_pyr_build_dev call), tracking addressed with from_first = 0 / to_first = B, device-resident inputs, and the
+    2000 x 2000 Hamming match of each pair -- every output of every pair against a single-pair oracle run."""
+    import importlib
+    import torch
+    bench = importlib.import_module("bench")
+    B = 3
+    W, H, NFEAT, LEVELS, DEPTH = bench.W, bench.H, bench.NFEAT, bench.LEVELS, bench.DEPTH
+    assert (W, H, NFEAT, LEVELS, DEPTH) == (640, 480, 2000, 4, 4)
+    dev = torch.device("cuda", 0)
+    A, Bf, pts, q, t = bench.make_inputs(torch, synth, B, dev, seed=5)
+    frames = torch.cat([A, Bf]).contiguous()
+    n = B * NFEAT
+    from_xy = torch.from_numpy(pts).to(dev)
+    to_xy = from_xy.clone()
+    fe.use_torch_stream()
+    try:
+        pyr = fe.pyramid(W, H, DEPTH, sfe.HESSIAN, 2 * B)
+        pyr.build(frames)
+        g = fe.track_fb(pyr, pyr, from_xy, to_xy, LEVELS, bench.THR, bench.MAXIT, bench.FB_MAX, n_per_pair=NFEAT, from_first=0, to_first=B)
+        q_d, t_d = torch.from_numpy(q.view(np.int32)).to(dev), torch.from_numpy(t.view(np.int32)).to(dev)
+        idx, dist, ok = fe.match_hamming256(q_d, t_d, *bench.RATIO, batch=B)
+        torch.cuda.synchronize()
+    finally:
+        fe.set_stream(None)
+    g = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in g.items()}
+    idx, dist, ok = (v.cpu().numpy() if hasattr(v, "cpu") else v for v in (idx, dist, ok))
+    fr = frames.cpu().numpy()
+    for p in range(B):
+        oa, ob = po.Pyramid(fr[p], DEPTH), po.Pyramid(fr[B + p], DEPTH)
+        for l in range(DEPTH):
+            assert_bits_equal(pyr.plane(l, p), oa.plane(l), "pair %d first frame level %d" % (p, l))
+            assert_bits_equal(pyr.plane(l, B + p), ob.plane(l), "pair %d second frame level %d" % (p, l))
+        sl = slice(p * NFEAT, (p + 1) * NFEAT)
+        o = po.hes_track_fb(oa, ob, pts[sl], pts[sl], LEVELS, bench.THR, bench.MAXIT, bench.FB_MAX)
+        for k in ("status_fwd", "status_bwd", "accepted"):
+            assert np.array_equal(g[k][sl], o[k]), (p, k)
+        assert_bits_equal(g["to_xy"][sl], o["to_xy"], "pair %d to_xy" % p)
+        assert_bits_equal(g["back_xy"][sl], o["back_xy"], "pair %d back_xy" % p)
+        assert int(g["steps"][sl].sum()) == o["newton_steps"]
+        oi, od, oo = po.hamming256_top2(q[sl], t[sl], *bench.RATIO)
+        assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od) and np.array_equal(ok[sl], oo)
+        assert o["accepted"].sum() > 0.5 * NFEAT
+
+
 @pytest.mark.parametrize("chunk", [2, 0, 5])
 def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
     """sfe_replay_pairs (host buffers, chunk-pipelined: copy | pyramid (three sets) | tracking | download streams):
