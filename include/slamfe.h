@@ -18,7 +18,9 @@
  *   - Per-feature status values are the reference's Status enum (hessian.h:48-52).
  *   - A context is bound to one GPU and one stream; calls on one context are stream-ordered
  *     and must not be issued from several host threads at once (the reference's Matcher is
- *     single-threaded too, main.cpp:490).
+ *     single-threaded too, main.cpp:490).  sfe_set_stream may switch streams between calls:
+ *     every tracker launch owns its work-queue counter, but the scratch buffers of the
+ *     host-pointer entries are shared, so those still assume one stream at a time.
  */
 #ifndef SLAMFE_H_
 #define SLAMFE_H_
@@ -97,7 +99,8 @@ int sfe_pyr_download(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int
  *   from_xy  [n][2]  in   template position in the `from` frame           (from_pt)
  *   to_xy    [n][2]  in   initial guess; out: tracked position, unchanged when the forward
  *                         track fails (hessian.h:262 semantics)             (to_pt)
- *   levels   [n] or NULL  pyramid levels to use per feature (3 or 6, matcher.cpp:227-229);
+ *   levels   [n] or NULL  pyramid levels to use per feature (3 or 6, matcher.cpp:227-229), each >= 1 (the host-pointer
+ *                         entries reject smaller values, the _dev entries track such a feature with 1 level);
  *                         NULL = default_levels for all
  *   thr, maxit, fb_max    0.001, 10, 0.3 in the reference (matcher.cpp:176,182,201)
  *   back_xy  [n][2]  out  backward-tracked position                       (back_pt)
@@ -107,13 +110,13 @@ int sfe_pyr_download(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int
  */
 int sfe_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
                  int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
-                 const int32_t* levels, int default_levels, float thr, int maxit, float fb_max,
+                 const int32_t* levels, int default_levels, float thr, int maxit, double fb_max,
                  float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted,
                  int32_t* steps);
 int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
                      int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
                      const int32_t* levels, int default_levels, float thr, int maxit,
-                     float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                     double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                      uint8_t* accepted, int32_t* steps);
 
 /* Replaces one-directional tracker->TrackFeature(stack, GetPatches(tmpl, tmpl_pt, levels), thr, maxit, &pt)
@@ -144,11 +147,11 @@ int sfe_brute_hessian(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const s
  * used (klt.h:409) and the coarse-level threshold is 50x (klt.h:413). */
 int sfe_klt_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
                      int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
-                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                     float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
                      int32_t* status_bwd, uint8_t* accepted, int32_t* steps);
 int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to,
                          int to_first, int n, int n_per_pair, const float* from_xy, float* to_xy,
-                         float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                         float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
                          int32_t* status_bwd, uint8_t* accepted, int32_t* steps);
 /* The symmetric-KLT normal equations of klt.h:286-353 at one point per feature:
  * out [n][24] = A(4) B(4) C(4) RS(2) VW(2) U(4) e(2) d(2), row-major 2x2 blocks. */
@@ -200,7 +203,8 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
 /* The host-side batching/stream layer: what Matcher::Track does per frame -- MakePyramid
  * (matcher.cpp:317) and the FindMatches tracking loop (matcher.cpp:208-271 -> :173-206) -- for
  * `npairs` independent (from, to) frame pairs of a replayed sequence (BASELINE config 4), host
- * buffers in and out.  The pairs are processed in chunks of `chunk_pairs` (<= 0: automatic) on a
+ * buffers in and out.  The pairs are processed in chunks of `chunk_pairs` (<= 0: automatic, an eighth of the call
+ * but at most 128 pairs, so device memory does not grow with the length of the replay) on a
  * stream pipeline (upload of chunk k+2 | pyramids of chunk k+1 | tracking of chunk k | download of
  * chunk k-1), so with pinned host buffers the PCIe transfers hide behind the kernels.
  *   from_bgr, to_bgr  npairs frames each, 8-bit BGR, row_stride / frame_stride in bytes
@@ -209,7 +213,7 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
 int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
                      const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
                      const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
-                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                     float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
                      int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
 
 /* The same pipeline for a replayed SEQUENCE (`./slam --load dir`, main.cpp:446-448): `nframes` consecutive frames in one
@@ -221,8 +225,57 @@ int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const ui
 int sfe_replay_sequence(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
                         const uint8_t* frames_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
                         const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
-                        float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd,
+                        float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
                         int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
+
+/* sfe_replay_sequence for frames in the camera's native format: packed YUYV, 2 bytes per pixel (w even), as the V4L2
+ * path receives them (video.cpp:136-139).  Every frame crosses PCIe as 2 instead of 3 bytes per pixel and is converted
+ * on the device with the integer arithmetic of video.cpp:187-223 (sfe_yuyv_to_bgr) before MakePyramid, so the results
+ * equal sfe_replay_sequence on the BGR frames that loop produces.  row_stride / frame_stride in bytes (>= 2 w). */
+int sfe_replay_sequence_yuyv(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
+                             const uint8_t* frames_yuyv, size_t row_stride, size_t frame_stride, int n_per_pair,
+                             const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                             float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
+                             int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs);
+
+/* ---- several GPUs of one box ----------------------------------------------------------------- */
+
+/* The path shards in two places (one sfe_ctx per GPU, one process or host thread per GPU):
+ *   frame pairs of a replayed sequence are independent units -- each rank replays the block sfe_shard_range gives it
+ *   with sfe_replay_sequence / sfe_replay_pairs, NO collective on the data path; sfe_allgather_rows collects the
+ *   per-feature result rows when the caller wants them in one place (the reference's map bookkeeping,
+ *   matcher.cpp:253-268, is host code and stays with the caller);
+ *   the descriptor matcher has one exchange: train set broadcast, query rows sharded, top-2 rows all-gathered.
+ * The reference is a single process with a single Matcher (main.cpp:490); these entries are what its C++ caller
+ * binds to spread a replay or a large match over the GPUs of a box.  NCCL (libnccl.so.2) is loaded at run time;
+ * the collectives run on the context's stream, ordered with the kernels. */
+
+/* Contiguous block [lo, hi) of n units owned by `rank` of `world` (blocks differ by at most one unit). */
+int sfe_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
+/* Communicator set-up: rank 0 obtains an id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by any
+ * means; every rank then calls sfe_dist_init (ncclCommInitRank on the context's device; collective, blocks until
+ * all ranks have called).  Alternatively sfe_dist_attach adopts an ncclComm_t the caller created for the context's
+ * device (passed as void*; it is not destroyed with the context). */
+int sfe_dist_unique_id(uint8_t* id128);
+int sfe_dist_init(sfe_ctx* ctx, const uint8_t* id128, int rank, int world);
+int sfe_dist_attach(sfe_ctx* ctx, void* nccl_comm, int rank, int world);
+int sfe_dist_shutdown(sfe_ctx* ctx);
+/* All-gather of row blocks of unequal length: this rank contributes rows [lo, hi) = sfe_shard_range(n_total) from
+ * local_dev (or NULL when they already sit at all_dev + lo * row_bytes); afterwards all_dev holds all n_total rows on
+ * every rank.  Device pointers; enqueued on the context's stream. */
+int sfe_allgather_rows_dev(sfe_ctx* ctx, const void* local_dev, size_t row_bytes, int64_t n_total, void* all_dev);
+/* sfe_match_hamming256 for nq_total query rows sharded over the ranks (BASELINE config 5): q_local holds THIS rank's
+ * rows [lo, hi) = sfe_shard_range(nq_total); t holds the nt train rows on rank train_root and is overwritten with them
+ * on the other ranks (ncclBroadcast); idx_all / dist_all [nq_total][2] and pass_all [nq_total] (may be NULL) receive the
+ * rows of ALL ranks (all-gather), identical to a single-GPU sfe_match_hamming256 of the whole problem.  The _dev
+ * variant takes device pointers and only enqueues; the host variant copies in, runs, copies out and synchronises
+ * (t may be NULL on ranks other than train_root). */
+int sfe_match_hamming256_sharded_dev(sfe_ctx* ctx, const uint32_t* q_local, int64_t nq_total, uint32_t* t, int nt,
+                                     int train_root, int ratio_num, int ratio_den, int max_dist, int32_t* idx_all,
+                                     int32_t* dist_all, uint8_t* pass_all);
+int sfe_match_hamming256_sharded(sfe_ctx* ctx, const uint32_t* q_local, int64_t nq_total, const uint32_t* t, int nt,
+                                 int train_root, int ratio_num, int ratio_den, int max_dist, int32_t* idx_all,
+                                 int32_t* dist_all, uint8_t* pass_all);
 
 /* ---- corner seeding (the step after tracking on keyframes) -------------------------------- */
 

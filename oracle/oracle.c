@@ -520,7 +520,7 @@ int orc_hes_track_feature(const orc_pyr* tmpl_pyr, float tx, float ty, const orc
 
 /* matcher.cpp:173-206 applied to n features. */
 int orc_hes_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float* from_xy,
-                     float* to_xy, const int* levels, float thr, int maxit, float fb_max,
+                     float* to_xy, const int* levels, float thr, int maxit, double fb_max,
                      float* back_xy, int* st_fwd, int* st_bwd, uint8_t* accepted,
                      orc_counters* c, int nthreads) {
   int64_t steps = 0, patches = 0;
@@ -542,7 +542,7 @@ int orc_hes_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float*
     if (ok) {
       float ddx = fx - bx, ddy = fy - by;
       double nrm = sqrt((double)ddx * ddx + (double)ddy * ddy);                       /* cv::norm */
-      if (nrm > (double)fb_max) ok = 0;                                               /* :201 */
+      if (nrm > fb_max) ok = 0;                                               /* :201 */
     }
     to_xy[2 * i] = tx; to_xy[2 * i + 1] = ty;
     if (back_xy) { back_xy[2 * i] = bx; back_xy[2 * i + 1] = by; }
@@ -942,7 +942,7 @@ int orc_klt_track_feature(const orc_pyr* tmpl_pyr, float tx, float ty, const orc
 }
 
 int orc_klt_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float* from_xy,
-                     float* to_xy, float thr, int maxit, float fb_max, float* back_xy, int* st_fwd,
+                     float* to_xy, float thr, int maxit, double fb_max, float* back_xy, int* st_fwd,
                      int* st_bwd, uint8_t* accepted, orc_counters* c, int nthreads) {
   int64_t steps = 0, patches = 0;
   int nacc = 0;
@@ -961,7 +961,7 @@ int orc_klt_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float*
     int ok = !(s1 || s2);
     if (ok) {
       float ddx = fx - bx, ddy = fy - by;
-      if (sqrt((double)ddx * ddx + (double)ddy * ddy) > (double)fb_max) ok = 0;
+      if (sqrt((double)ddx * ddx + (double)ddy * ddy) > fb_max) ok = 0;
     }
     to_xy[2 * i] = tx; to_xy[2 * i + 1] = ty;
     if (back_xy) { back_xy[2 * i] = bx; back_xy[2 * i + 1] = by; }

@@ -105,7 +105,7 @@ int orc_hes_track_feature(const orc_pyr* tmpl_pyr, float tx, float ty, const orc
                           orc_counters* c);                             /* GetPatches + TrackFeature */
 /* matcher.cpp:173-206 for n features; to_xy is in (seed) / out; returns #accepted */
 int orc_hes_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float* from_xy,
-                     float* to_xy, const int* levels, float thr, int maxit, float fb_max,
+                     float* to_xy, const int* levels, float thr, int maxit, double fb_max,
                      float* back_xy, int* st_fwd, int* st_bwd, uint8_t* accepted,
                      orc_counters* c, int nthreads);
 
@@ -117,7 +117,7 @@ void orc_klt_system(const orc_pyr* tmpl_pyr, float tx, float ty, const orc_pyr* 
 int orc_klt_track_feature(const orc_pyr* tmpl_pyr, float tx, float ty, const orc_pyr* search,
                           float thr, int maxit, float* x, float* y, orc_counters* c);
 int orc_klt_track_fb(const orc_pyr* from, const orc_pyr* to, int n, const float* from_xy,
-                     float* to_xy, float thr, int maxit, float fb_max, float* back_xy, int* st_fwd,
+                     float* to_xy, float thr, int maxit, double fb_max, float* back_xy, int* st_fwd,
                      int* st_bwd, uint8_t* accepted, orc_counters* c, int nthreads);
 
 /* ---- P3: BruteTracker ------------------------------------------------------ */

@@ -77,14 +77,14 @@ def lib(fast=False, native=False):
     L.orc_hes_track_feature.argtypes = [vp, C.c_float, C.c_float, vp, C.c_int, C.c_float, C.c_int, f32p, f32p,
                                         C.POINTER(Counters)]
     L.orc_hes_track_feature.restype = C.c_int
-    L.orc_hes_track_fb.argtypes = [vp, vp, C.c_int, f32p, f32p, i32p, C.c_float, C.c_int, C.c_float, f32p, i32p,
+    L.orc_hes_track_fb.argtypes = [vp, vp, C.c_int, f32p, f32p, i32p, C.c_float, C.c_int, C.c_double, f32p, i32p,
                                    i32p, u8p, C.POINTER(Counters), C.c_int]
     L.orc_hes_track_fb.restype = C.c_int
     L.orc_klt_system.argtypes = [vp, C.c_float, C.c_float, vp, C.c_int, C.c_float, C.c_float, f32p]
     L.orc_klt_track_feature.argtypes = [vp, C.c_float, C.c_float, vp, C.c_float, C.c_int, f32p, f32p,
                                         C.POINTER(Counters)]
     L.orc_klt_track_feature.restype = C.c_int
-    L.orc_klt_track_fb.argtypes = [vp, vp, C.c_int, f32p, f32p, C.c_float, C.c_int, C.c_float, f32p, i32p, i32p,
+    L.orc_klt_track_fb.argtypes = [vp, vp, C.c_int, f32p, f32p, C.c_float, C.c_int, C.c_double, f32p, i32p, i32p,
                                    u8p, C.POINTER(Counters), C.c_int]
     L.orc_klt_track_fb.restype = C.c_int
     L.orc_brute_search_best.argtypes = [vp, C.c_int, f32p, C.c_float, C.c_float, C.c_float, C.c_float, f32p,
@@ -246,7 +246,7 @@ def hes_track_fb(pfrom, pto, from_xy, seed_xy, levels, thr=0.001, maxit=10, fb_m
     acc = np.empty(n, np.uint8)
     cnt = Counters(0, 0)
     pfrom._L.orc_hes_track_fb(pfrom.h, pto.h, n, _p(from_xy, C.c_float), _p(to_xy, C.c_float),
-                              _p(levels, C.c_int32), C.c_float(thr), maxit, C.c_float(fb_max),
+                              _p(levels, C.c_int32), C.c_float(thr), maxit, C.c_double(fb_max),
                               _p(back, C.c_float), _p(s1, C.c_int32), _p(s2, C.c_int32), _p(acc, C.c_uint8),
                               C.byref(cnt), nthreads)
     return dict(to_xy=to_xy, back_xy=back, status_fwd=s1, status_bwd=s2, accepted=acc,
@@ -270,7 +270,7 @@ def klt_track_fb(pfrom, pto, from_xy, seed_xy, thr=0.001, maxit=10, fb_max=0.3, 
     acc = np.empty(n, np.uint8)
     cnt = Counters(0, 0)
     pfrom._L.orc_klt_track_fb(pfrom.h, pto.h, n, _p(from_xy, C.c_float), _p(to_xy, C.c_float), C.c_float(thr),
-                              maxit, C.c_float(fb_max), _p(back, C.c_float), _p(s1, C.c_int32),
+                              maxit, C.c_double(fb_max), _p(back, C.c_float), _p(s1, C.c_int32),
                               _p(s2, C.c_int32), _p(acc, C.c_uint8), C.byref(cnt), nthreads)
     return dict(to_xy=to_xy, back_xy=back, status_fwd=s1, status_bwd=s2, accepted=acc,
                 newton_steps=cnt.newton_steps, patches=cnt.patches)

@@ -329,7 +329,7 @@ def hes_track_fb(pfrom, pto, from_xy, seed_xy, levels, thr=0.001, maxit=10, fb_m
         ok = not (s1 or s2)
         if ok:
             ddx, ddy = f32(fx - bx), f32(fy - by)
-            if math.sqrt(float(ddx) * float(ddx) + float(ddy) * float(ddy)) > float(f32(fb_max)):
+            if math.sqrt(float(ddx) * float(ddx) + float(ddy) * float(ddy)) > float(fb_max):
                 ok = False
         out["to_xy"][i] = (tx, ty)
         out["back_xy"][i] = (bx, by)
@@ -497,7 +497,7 @@ def klt_track_fb(pfrom, pto, from_xy, thr=0.001, maxit=10, fb_max=0.3, traces=No
         ok = not (s1 or s2)
         if ok:
             ddx, ddy = f32(fx - bx), f32(fy - by)
-            if math.sqrt(float(ddx) * float(ddx) + float(ddy) * float(ddy)) > float(f32(fb_max)):
+            if math.sqrt(float(ddx) * float(ddx) + float(ddy) * float(ddy)) > float(fb_max):
                 ok = False
         out["to_xy"][i] = (tx, ty)
         out["back_xy"][i] = (bx, by)

@@ -36,8 +36,11 @@ EXPORTS = [
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
-    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_good_features", "sfe_good_features_dev",
+    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_replay_sequence_yuyv", "sfe_good_features",
+    "sfe_good_features_dev",
     "sfe_seed_features", "sfe_seed_features_dev", "sfe_yuyv_to_bgr", "sfe_yuyv_to_bgr_dev",
+    "sfe_shard_range", "sfe_dist_unique_id", "sfe_dist_init", "sfe_dist_attach", "sfe_dist_shutdown", "sfe_allgather_rows_dev",
+    "sfe_match_hamming256_sharded_dev", "sfe_match_hamming256_sharded",
 ]
 
 
@@ -98,7 +101,8 @@ def lib():
     L.sfe_pyr_build.argtypes = [vp, vp, vp, sz, sz, i32, i32]
     L.sfe_pyr_build_dev.argtypes = [vp, vp, vp, sz, sz, i32, i32]
     L.sfe_pyr_download.argtypes = [vp, vp, i32, i32, i32, vp]
-    trk = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp, vp, vp]
+    f64 = C.c_double   # fb_max: matcher.cpp:201 compares with the double literal 0.3
+    trk = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, f32, i32, f64, vp, vp, vp, vp, vp]
     L.sfe_track_fb.argtypes = trk
     L.sfe_track_fb_dev.argtypes = trk
     one = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, f32, i32, vp, vp]
@@ -106,7 +110,7 @@ def lib():
     L.sfe_track_dev.argtypes = one
     L.sfe_get_patches.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.sfe_brute_hessian.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp]
-    klt = [vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, f32, vp, vp, vp, vp, vp]
+    klt = [vp, vp, i32, vp, i32, i32, i32, vp, vp, f32, i32, f64, vp, vp, vp, vp, vp]
     L.sfe_klt_track_fb.argtypes = klt
     L.sfe_klt_track_fb_dev.argtypes = klt
     L.sfe_klt_system.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp]
@@ -123,10 +127,21 @@ def lib():
     L.sfe_seed_features_dev.argtypes = seed
     L.sfe_yuyv_to_bgr.argtypes = [vp, vp, sz, vp]
     L.sfe_yuyv_to_bgr_dev.argtypes = [vp, vp, sz, vp]
-    L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
+    L.sfe_replay_pairs.argtypes = [vp, i32, i32, i32, i32, vp, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f64, vp, vp, vp,
                                    vp, vp, i32]
-    L.sfe_replay_sequence.argtypes = [vp, i32, i32, i32, i32, i32, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f32, vp, vp, vp,
+    L.sfe_replay_sequence.argtypes = [vp, i32, i32, i32, i32, i32, vp, sz, sz, i32, vp, vp, vp, i32, f32, i32, f64, vp, vp, vp,
                                       vp, vp, i32]
+    L.sfe_replay_sequence_yuyv.argtypes = L.sfe_replay_sequence.argtypes
+    i64 = C.c_int64
+    L.sfe_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.sfe_dist_unique_id.argtypes = [vp]
+    L.sfe_dist_init.argtypes = [vp, vp, i32, i32]
+    L.sfe_dist_attach.argtypes = [vp, vp, i32, i32]
+    L.sfe_dist_shutdown.argtypes = [vp]
+    L.sfe_allgather_rows_dev.argtypes = [vp, vp, sz, i64, vp]
+    shd = [vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.sfe_match_hamming256_sharded_dev.argtypes = shd
+    L.sfe_match_hamming256_sharded.argtypes = shd
     _lib = L
     return L
 
@@ -365,11 +380,12 @@ class FrontEnd:
 
     def replay_sequence(self, frames, pair_stride, from_xy, seed_xy, depth, levels=3, thr=0.001, maxit=10, fb_max=0.3,
                         n_per_pair=None, chunk_pairs=0, out=None, want_steps=True):
-        """frames: (nframes,H,W,3) uint8 host array of a replayed sequence; pair i = (frame i, frame i + pair_stride).
+        """frames: (nframes,H,W,3) uint8 BGR host array of a replayed sequence -- or (nframes,H,W,2) packed YUYV, the
+        camera's native format (sfe_replay_sequence_yuyv); pair i = (frame i, frame i + pair_stride).
         from_xy/seed_xy: ((nframes - pair_stride) * n_per_pair, 2) float32 host arrays, pair-major."""
         nframes, H, W, ch = frames.shape
         npairs = max(nframes - int(pair_stride), 0)
-        assert ch == 3 and (frames.is_contiguous() if _is_torch(frames) else frames.flags.c_contiguous)
+        assert ch in (2, 3) and (frames.is_contiguous() if _is_torch(frames) else frames.flags.c_contiguous)
         from_xy = from_xy if _is_torch(from_xy) else _np(from_xy, np.float32).reshape(-1, 2)
         n = from_xy.shape[0]
         npp = n // max(npairs, 1) if n_per_pair is None else int(n_per_pair)
@@ -382,11 +398,12 @@ class FrontEnd:
         lv_arr = None
         if levels is not None and not np.isscalar(levels):
             lv_arr = _np(levels, np.int32)
-        self._chk(self.L.sfe_replay_sequence(self.h, W, H, depth, nframes, int(pair_stride), _ptr(frames), 3 * W, 3 * W * H,
-                                             max(npp, 1), _ptr(from_xy), _ptr(out["to_xy"]), _ptr(lv_arr),
-                                             int(levels) if lv_arr is None else 3, thr, maxit, fb_max, _ptr(out["back_xy"]),
-                                             _ptr(out["status_fwd"]), _ptr(out["status_bwd"]), _ptr(out["accepted"]),
-                                             _ptr(out.get("steps")), int(chunk_pairs)))
+        fn = self.L.sfe_replay_sequence if ch == 3 else self.L.sfe_replay_sequence_yuyv
+        self._chk(fn(self.h, W, H, depth, nframes, int(pair_stride), _ptr(frames), ch * W, ch * W * H,
+                     max(npp, 1), _ptr(from_xy), _ptr(out["to_xy"]), _ptr(lv_arr),
+                     int(levels) if lv_arr is None else 3, thr, maxit, fb_max, _ptr(out["back_xy"]),
+                     _ptr(out["status_fwd"]), _ptr(out["status_bwd"]), _ptr(out["accepted"]),
+                     _ptr(out.get("steps")), int(chunk_pairs)))
         return out
 
     # ---- corner seeding (matcher.cpp:313 + :123-130: RGB2GRAY + goodFeaturesToTrack)
@@ -444,6 +461,62 @@ class FrontEnd:
         return arr
 
     # ---- P4
+    # ---- several GPUs of one box (include/slamfe.h; NCCL inside the library, one FrontEnd per rank)
+    def dist_init(self, rank, world, id128=None, exchange=None):
+        """Creates this rank's NCCL communicator inside the library.  The 128-byte id comes from rank 0
+        (dist_unique_id()); `exchange` is a callable that broadcasts a uint8 numpy array from rank 0 (plumbing: e.g. a
+        torch.distributed / gloo broadcast) and is used when id128 is not given."""
+        if id128 is None:
+            id128 = np.zeros(128, np.uint8)
+            if rank == 0:
+                self._chk(self.L.sfe_dist_unique_id(_ptr(id128)))
+            if world > 1:
+                id128 = exchange(id128)
+        id128 = np.ascontiguousarray(id128, dtype=np.uint8)
+        self._chk(self.L.sfe_dist_init(self.h, _ptr(id128), int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def dist_shutdown(self):
+        self._chk(self.L.sfe_dist_shutdown(self.h))
+
+    def shard_range(self, n, rank=None, world=None):
+        lo, hi = C.c_int64(), C.c_int64()
+        rc = self.L.sfe_shard_range(int(n), self.rank if rank is None else rank, self.world if world is None else world,
+                                    C.byref(lo), C.byref(hi))
+        if rc:
+            raise SlamFEError("sfe_shard_range: bad arguments")
+        return lo.value, hi.value
+
+    def match_hamming256_sharded(self, q_local, nq_total, t, nt, train_root=0, ratio_num=4, ratio_den=5, max_dist=256, out=None):
+        """q_local: this rank's query rows; t: (nt, 8) train rows (valid on train_root, overwritten elsewhere).
+        CUDA tensors -> device entry (enqueues on the context's stream), numpy -> host entry.  Returns the gathered
+        (idx[nq_total,2], dist[nq_total,2], pass[nq_total])."""
+        dev = _is_torch(q_local) and q_local.is_cuda
+        if dev:
+            import torch
+            if out is None:
+                out = (torch.empty((nq_total, 2), dtype=torch.int32, device=q_local.device),
+                       torch.empty((nq_total, 2), dtype=torch.int32, device=q_local.device),
+                       torch.empty(nq_total, dtype=torch.uint8, device=q_local.device))
+            fn = self.L.sfe_match_hamming256_sharded_dev
+        else:
+            q_local = np.ascontiguousarray(q_local).view(np.uint32).reshape(-1, 8)
+            t = None if t is None else np.ascontiguousarray(t).view(np.uint32).reshape(-1, 8)
+            out = (np.empty((nq_total, 2), np.int32), np.empty((nq_total, 2), np.int32), np.empty(nq_total, np.uint8))
+            fn = self.L.sfe_match_hamming256_sharded
+        self._chk(fn(self.h, _ptr(q_local), int(nq_total), _ptr(t), int(nt), int(train_root), ratio_num, ratio_den, max_dist,
+                     _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
+    def allgather_rows(self, local, n_total, out=None):
+        """local: this rank's rows (CUDA tensor [m, ...]); returns all n_total rows on every rank."""
+        import torch
+        row = int(np.prod(local.shape[1:])) * local.element_size() if local.ndim > 1 else local.element_size()
+        if out is None:
+            out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self._chk(self.L.sfe_allgather_rows_dev(self.h, _ptr(local.contiguous()), row, int(n_total), _ptr(out)))
+        return out
+
     def match_hamming256_async(self, q, t, out, ratio_num=4, ratio_den=5, max_dist=256, batch=1):
         """Host arrays (pinned for real asynchrony); only enqueues -- call sync() before reading `out`."""
         nq, nt = q.shape[0] // batch, t.shape[0] // batch

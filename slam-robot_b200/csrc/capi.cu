@@ -92,6 +92,9 @@ namespace {
 template <class Launch>
 int track_host(sfe_ctx* ctx, int n, const float* from_xy, float* to_xy, const int32_t* levels, float* back_xy,
                int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps, Launch launch) {
+  if (levels)  // hessian.h:249: lvls = min(stack.size(), patches.size()) >= 1 for every call the reference makes
+    for (int i = 0; i < n; ++i)
+      if (levels[i] < 1) return fail(ctx, SFE_ERR_INVALID, "%s", "levels[] entries must be >= 1");
   size_t need = padded(8 * (size_t)n) * 3 + padded(4 * (size_t)n) * 4 + padded(n);
   int rc = ensure_scratch(ctx, need);
   if (rc) return rc;
@@ -200,7 +203,7 @@ int sfe_create(int device, sfe_ctx** out) {
   ctx->stream = ctx->own_stream;
   build_mask(ctx->h_mask);
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
-  if (cudaMalloc(&ctx->d_counter, 256) != cudaSuccess || cudaMalloc(&ctx->d_mask, sizeof(ctx->h_mask)) != cudaSuccess ||
+  if (cudaMalloc(&ctx->d_counter, 64 * SFE_COUNTER_SLOTS) != cudaSuccess || cudaMalloc(&ctx->d_mask, sizeof(ctx->h_mask)) != cudaSuccess ||
       cudaMemcpy(ctx->d_mask, ctx->h_mask, sizeof(ctx->h_mask), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -215,6 +218,7 @@ void sfe_destroy(sfe_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   sfe_replay_release(ctx);
+  sfe_dist_release(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ham_ws) cudaFree(ctx->ham_ws);
@@ -389,7 +393,7 @@ int sfe_pyr_download(sfe_ctx* ctx, const sfe_pyr* pyr, int frame, int level, int
 
 int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
                      int n_per_pair, const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
-                     float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                     float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                      uint8_t* accepted, int32_t* steps) {
   if (!ctx) return SFE_ERR_INVALID;
   int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
@@ -400,13 +404,13 @@ int sfe_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sf
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, levels, default_levels, thr, maxit, fb_max,
               back_xy, status_fwd, status_bwd, accepted, steps, 2};
-  return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "track launch: %s");
+  return launched(ctx, launch_track_hessian(from->view, to->view, a, ctx->d_mask, sfe_next_counter(ctx), ctx->num_sms, ctx->stream), "track launch: %s");
 }
 
 
 int sfe_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
                  int n_per_pair, const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
-                 float thr, int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                 float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                  uint8_t* accepted, int32_t* steps) {
   if (!ctx) return SFE_ERR_INVALID;
   if (n == 0) return SFE_SUCCESS;
@@ -429,11 +433,11 @@ int sfe_track_dev(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_first, const sfe_p
   if (tmpl->flavor != search->flavor || tmpl->flavor == SFE_BRUTE)
     return fail(ctx, SFE_ERR_INVALID, "%s", "sfe_track needs two SFE_HESSIAN or two SFE_KLT pyramids");
   if (use_device(ctx)) return SFE_ERR_CUDA;
-  TrackArgs a{n, n_per_pair, tmpl_first, search_first, tmpl_xy, xy, levels, default_levels, thr, maxit, 0.f,
+  TrackArgs a{n, n_per_pair, tmpl_first, search_first, tmpl_xy, xy, levels, default_levels, thr, maxit, 0.,
               nullptr, status, nullptr, nullptr, steps, 1};
   int r = tmpl->flavor == SFE_HESSIAN
-              ? launch_track_hessian(tmpl->view, search->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream)
-              : launch_track_klt(tmpl->view, search->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream);
+              ? launch_track_hessian(tmpl->view, search->view, a, ctx->d_mask, sfe_next_counter(ctx), ctx->num_sms, ctx->stream)
+              : launch_track_klt(tmpl->view, search->view, a, ctx->d_mask, sfe_next_counter(ctx), ctx->num_sms, ctx->stream);
   return launched(ctx, r, "track launch: %s");
 }
 
@@ -492,7 +496,7 @@ int sfe_brute_hessian(sfe_ctx* ctx, const sfe_pyr* tmpl, int tmpl_frame, const s
 /* ---- P2 ---------------------------------------------------------------------------------- */
 
 int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
-                         int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, float fb_max,
+                         int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, double fb_max,
                          float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps) {
   if (!ctx) return SFE_ERR_INVALID;
   int rc = check_pairs(ctx, from, from_first, to, to_first, n, n_per_pair);
@@ -503,11 +507,11 @@ int sfe_klt_track_fb_dev(sfe_ctx* ctx, const sfe_pyr* from, int from_first, cons
   if (use_device(ctx)) return SFE_ERR_CUDA;
   TrackArgs a{n, n_per_pair, from_first, to_first, from_xy, to_xy, nullptr, from->view.depth, thr, maxit, fb_max,
               back_xy, status_fwd, status_bwd, accepted, steps, 2};
-  return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, ctx->d_counter, ctx->num_sms, ctx->stream), "klt launch: %s");
+  return launched(ctx, launch_track_klt(from->view, to->view, a, ctx->d_mask, sfe_next_counter(ctx), ctx->num_sms, ctx->stream), "klt launch: %s");
 }
 
 int sfe_klt_track_fb(sfe_ctx* ctx, const sfe_pyr* from, int from_first, const sfe_pyr* to, int to_first, int n,
-                     int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, float fb_max,
+                     int n_per_pair, const float* from_xy, float* to_xy, float thr, int maxit, double fb_max,
                      float* back_xy, int32_t* status_fwd, int32_t* status_bwd, uint8_t* accepted, int32_t* steps) {
   if (!ctx) return SFE_ERR_INVALID;
   if (n == 0) return SFE_SUCCESS;
@@ -688,9 +692,12 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
 /* ---- corner seeding -------------------------------------------------- */
 
 namespace {
-int gftt_cap(int w, int h) {  // candidate capacity per frame: a power of two >= w*h/8 (the bitonic sort pads to one)
+int gftt_cap(int w, int h) {  // candidate capacity per frame: a power of two (the bitonic sort pads to one) that holds the
+  // worst case of distinct responses -- 3x3 maxima cannot be 8-neighbours of each other unless they are exactly equal,
+  // so at most one per 2x2 block: a densely textured frame proceeds as it does in the reference instead of failing with
+  // an overflow (only plateaus of bit-identical non-zero responses can still exceed it; that is reported as an error)
   int cap = 1024;
-  while (cap < (w / 8 + 1) * h) cap <<= 1;
+  while (cap < ((w + 1) / 2) * ((h + 1) / 2)) cap <<= 1;
   return cap;
 }
 size_t gftt_ws_bytes(int w, int h, int count) {

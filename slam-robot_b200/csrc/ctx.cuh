@@ -3,13 +3,17 @@
 #include "sfe_common.cuh"
 
 struct sfe_replay;  // replay.cu: the chunk pipeline's streams, events and staging buffers
+struct sfe_dist;    // dist.cu: the NCCL communicator of the multi-GPU entries
 
 struct sfe_ctx {
   int device;
   cudaStream_t own_stream;
   cudaStream_t stream;
   float* d_mask;
-  int* d_counter;  // work-queue head of the persistent tracking kernels
+  // work-queue heads of the persistent tracking kernels: a ring of 64-byte slots, one per launch, so that trackers
+  // enqueued on different streams of one context (sfe_set_stream, the replay pipeline) never share a counter
+  int* d_counter;
+  unsigned counter_seq;
   int num_sms;
   float h_mask[SFE_PLEN];
   // grow-on-demand device scratch for the host-pointer entry points
@@ -28,6 +32,7 @@ struct sfe_ctx {
   bool ham_pending;
   int64_t launches;
   sfe_replay* replay;  // lazily created by sfe_replay_pairs
+  sfe_dist* dist;      // sfe_dist_init / sfe_dist_attach
   void* gftt_ws;   // corner-seeding workspace: response maps, maxima, candidate keys
   size_t gftt_cap;
   char err[512];
@@ -45,3 +50,7 @@ struct sfe_pyr {
 
 
 void sfe_replay_release(sfe_ctx* ctx);  // replay.cu
+void sfe_dist_release(sfe_ctx* ctx);    // dist.cu
+
+constexpr int SFE_COUNTER_SLOTS = 64;
+inline int* sfe_next_counter(sfe_ctx* ctx) { return ctx->d_counter + 16 * (ctx->counter_seq++ % SFE_COUNTER_SLOTS); }

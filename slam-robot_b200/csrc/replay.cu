@@ -22,8 +22,9 @@
 struct sfe_replay {
   cudaStream_t copy_stream, out_stream, compute2, pyr_stream;  // tracking alternates between the context's stream and compute2
   cudaEvent_t copied[2], consumed[2], built[3], tracked[3], drained;
-  int w, h, depth, chunk;  // geometry the frame buffers / pyramids were built for
+  int w, h, depth, chunk;  // geometry the frame buffers / pyramids were built for (calls with chunk <= this reuse them)
   uint8_t* d_frames[2];    // per buffer: the c from-frames of a chunk followed by its c to-frames (c <= chunk)
+  uint8_t* d_raw[2];       // YUYV input only: the frames as uploaded, converted into d_frames on the pyramid stream
   sfe_pyr* pyr[3];         // pyramid sets of 2 * chunk slots (from-frames, then to-frames): chunk k uses set k % 3
   size_t n_cap;            // feature capacity of the arrays below
   float *d_from, *d_to, *d_back;
@@ -33,8 +34,10 @@ struct sfe_replay {
 
 namespace {
 
+thread_local const char* g_entry = "sfe_replay_pairs";  // the entry point the error text names
+
 int rfail(sfe_ctx* c, int code, const char* what, cudaError_t e) {
-  snprintf(c->err, sizeof(c->err), "sfe_replay_pairs: %s%s%s", what, e != cudaSuccess ? ": " : "",
+  snprintf(c->err, sizeof(c->err), "%s: %s%s%s", g_entry, what, e != cudaSuccess ? ": " : "",
            e != cudaSuccess ? cudaGetErrorString(e) : "");
   return code;
 }
@@ -48,8 +51,9 @@ int rfail(sfe_ctx* c, int code, const char* what, cudaError_t e) {
 void free_geometry(sfe_replay* r) {
   for (int b = 0; b < 3; ++b) {
     if (b < 2 && r->d_frames[b]) cudaFree(r->d_frames[b]);
+    if (b < 2 && r->d_raw[b]) cudaFree(r->d_raw[b]);
     if (r->pyr[b]) sfe_pyr_destroy(r->pyr[b]);
-    if (b < 2) r->d_frames[b] = nullptr;
+    if (b < 2) r->d_frames[b] = r->d_raw[b] = nullptr;
     r->pyr[b] = nullptr;
   }
   r->w = r->h = r->depth = r->chunk = 0;
@@ -65,7 +69,7 @@ void free_features(sfe_replay* r) {
   r->n_cap = 0;
 }
 
-int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
+int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n, bool yuyv) {
   sfe_replay* r = ctx->replay;
   if (!r) {
     r = new (std::nothrow) sfe_replay();
@@ -86,7 +90,7 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
     }
     RCU(cudaEventCreateWithFlags(&r->drained, cudaEventDisableTiming));
   }
-  if (r->w != w || r->h != h || r->depth != depth || r->chunk != chunk) {
+  if (r->w != w || r->h != h || r->depth != depth || r->chunk < chunk) {   // smaller chunks reuse the buffers
     RCU(cudaStreamSynchronize(ctx->stream));
     free_geometry(r);
     for (int b = 0; b < 3; ++b) {
@@ -96,6 +100,12 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
       if (rc) return rc;
     }
     r->w = w; r->h = h; r->depth = depth; r->chunk = chunk;
+  }
+  if (yuyv && !r->d_raw[0]) {
+    for (int b = 0; b < 2; ++b) {
+      cudaError_t e = cudaMalloc(&r->d_raw[b], (size_t)2 * r->chunk * 2 * w * h);
+      if (e != cudaSuccess) return rfail(ctx, SFE_ERR_NOMEM, "cudaMalloc(YUYV staging)", e);
+    }
   }
   if (n > r->n_cap) {
     RCU(cudaStreamSynchronize(ctx->stream));
@@ -117,8 +127,8 @@ int ensure(sfe_ctx* ctx, int w, int h, int depth, int chunk, size_t n) {
 }
 
 int upload_frames(sfe_ctx* ctx, uint8_t* dst, const uint8_t* src, int w, int h, size_t row_stride, size_t frame_stride,
-                  int count, cudaStream_t s) {
-  const size_t dense_row = (size_t)3 * w, dense_frame = dense_row * h;
+                  int count, cudaStream_t s, int bpp = 3) {
+  const size_t dense_row = (size_t)bpp * w, dense_frame = dense_row * h;
   if (row_stride == dense_row && (frame_stride == dense_frame || count == 1)) {
     RCU(cudaMemcpyAsync(dst, src, dense_frame * count, cudaMemcpyHostToDevice, s));
   } else {
@@ -159,24 +169,31 @@ namespace {
 int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride, const uint8_t* from_bgr,
                const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
                const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
-               int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
-               uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+               int maxit, double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+               uint8_t* accepted, int32_t* steps, int chunk_pairs, bool yuyv = false) {
   if (!ctx) return SFE_ERR_INVALID;
   if (npairs == 0) return SFE_SUCCESS;
+  const int bpp = yuyv ? 2 : 3;
   if (w < 1 || h < 1 || depth < 1 || depth > SFE_MAX_LEVELS || npairs < 0 || n_per_pair < 1 || !from_bgr ||
       (seq_stride == 0 && !to_bgr) || seq_stride < 0 || !from_xy || !to_xy || default_levels < 1 || maxit < 0 ||
-      row_stride < (size_t)3 * w)
+      row_stride < (size_t)bpp * w || (yuyv && ((w & 1) || ((size_t)w * h) % 4)))
     return rfail(ctx, SFE_ERR_INVALID, "bad arguments", cudaSuccess);
+  if (levels)
+    for (size_t i = 0; i < (size_t)npairs * n_per_pair; ++i)
+      if (levels[i] < 1) return rfail(ctx, SFE_ERR_INVALID, "levels[] entries must be >= 1", cudaSuccess);
   RCU(cudaSetDevice(ctx->device));
   // chunk size: default = an eighth of the batch (at least 8 pairs so that the kernels still fill the GPU; measured
-  // best on B200 for 128 VGA pairs); the first chunk is a quarter of that, so compute starts after a short upload
+  // best on B200 for 128 and 512 VGA pairs) but at most 128 pairs -- three pyramid sets and two staging buffers of
+  // 2 * chunk frames each are 1.4 GB then, whatever the length of the replay; the first chunk is a quarter of
+  // that, so compute starts after a short upload
   int chunk = chunk_pairs > 0 ? chunk_pairs : (npairs + 7) / 8;
   if (chunk_pairs <= 0 && chunk < 8) chunk = 8;
+  if (chunk_pairs <= 0 && chunk > 128) chunk = 128;
   if (chunk > npairs) chunk = npairs;
   if (chunk < seq_stride) chunk = seq_stride;   // a chunk's c + seq_stride frames must fit the 2 * chunk staging slots
   const int first_chunk = chunk >= 16 ? chunk / 4 : chunk;
   const size_t n = (size_t)npairs * n_per_pair;
-  int rc = ensure(ctx, w, h, depth, chunk, n);
+  int rc = ensure(ctx, w, h, depth, chunk, n, yuyv);
   if (rc) return rc;
   sfe_replay* r = ctx->replay;
   cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream, ps = r->pyr_stream;
@@ -204,16 +221,23 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
     // independent pairs: the c from-frames, then the c to-frames; sequence: the c + seq_stride frames the chunk's pairs touch
     const int nbuild = seq_stride ? c + seq_stride : 2 * c, to_first = seq_stride ? seq_stride : c;
-    rc = upload_frames(ctx, r->d_frames[b], from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride,
-                       seq_stride ? nbuild : c, xs);
+    uint8_t* up = yuyv ? r->d_raw[b] : r->d_frames[b];
+    const size_t up_frame = (size_t)bpp * w * h;
+    rc = upload_frames(ctx, up, from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride,
+                       seq_stride ? nbuild : c, xs, bpp);
     if (!rc && !seq_stride)
-      rc = upload_frames(ctx, r->d_frames[b] + (size_t)c * dense_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
-                         row_stride, frame_stride, c, xs);
+      rc = upload_frames(ctx, up + (size_t)c * up_frame, to_bgr + (size_t)p0 * frame_stride, w, h,
+                         row_stride, frame_stride, c, xs, bpp);
     if (rc) return rc;
     RCU(cudaEventRecord(r->copied[b], xs));
     // ---- pyramid stream: the pyramids of the chunk's frames into set k % 3 (free once chunk k-3 has been tracked)
     RCU(cudaStreamWaitEvent(ps, r->copied[b], 0));
     if (k >= 3) RCU(cudaStreamWaitEvent(ps, r->tracked[set], 0));
+    if (yuyv) {  // video.cpp:187-223 on the device: the staging buffer then holds the BGR frames MakePyramid takes
+      int nc = launch_yuyv_to_bgr(r->d_raw[b], (size_t)nbuild * w * h, r->d_frames[b], ps);
+      if (nc < 0) return rfail(ctx, SFE_ERR_CUDA, "yuyv_to_bgr launch", (cudaError_t)(-nc));
+      ctx->launches += nc;
+    }
     // one build for the frames of the chunk: slots [0, c) the from-frames, [to_first, to_first + c) the to-frames
     int nl = launch_pyr_build(r->pyr[set]->view, SFE_HESSIAN, r->d_frames[b], (size_t)3 * w, dense_frame, 0, nbuild, ps);
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "pyramid launch", (cudaError_t)(-nl));
@@ -226,8 +250,7 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     const int nf = c * n_per_pair;
     TrackArgs ta{nf, n_per_pair, 0, to_first, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
                  thr, maxit, fb_max, r->d_back + 2 * f0, r->d_s1 + f0, r->d_s2 + f0, r->d_acc + f0, r->d_steps + f0, 2};
-    nl = launch_track_hessian(r->pyr[set]->view, r->pyr[set]->view, ta, ctx->d_mask, ctx->d_counter + 16 * (1 + b),
-                              ctx->num_sms, cs);
+    nl = launch_track_hessian(r->pyr[set]->view, r->pyr[set]->view, ta, ctx->d_mask, sfe_next_counter(ctx), ctx->num_sms, cs);
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "track launch", (cudaError_t)(-nl));
     ctx->launches += nl;
     RCU(cudaEventRecord(r->tracked[set], cs));
@@ -253,8 +276,9 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
 extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npairs, const uint8_t* from_bgr,
                                 const uint8_t* to_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
                                 const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
-                                int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                                int maxit, double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                                 uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+  g_entry = "sfe_replay_pairs";
   return replay_run(ctx, w, h, depth, npairs, 0, from_bgr, to_bgr, row_stride, frame_stride, n_per_pair, from_xy, to_xy, levels,
                     default_levels, thr, maxit, fb_max, back_xy, status_fwd, status_bwd, accepted, steps, chunk_pairs);
 }
@@ -262,12 +286,27 @@ extern "C" int sfe_replay_pairs(sfe_ctx* ctx, int w, int h, int depth, int npair
 extern "C" int sfe_replay_sequence(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
                                    const uint8_t* frames_bgr, size_t row_stride, size_t frame_stride, int n_per_pair,
                                    const float* from_xy, float* to_xy, const int32_t* levels, int default_levels, float thr,
-                                   int maxit, float fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
+                                   int maxit, double fb_max, float* back_xy, int32_t* status_fwd, int32_t* status_bwd,
                                    uint8_t* accepted, int32_t* steps, int chunk_pairs) {
   if (!ctx) return SFE_ERR_INVALID;
+  g_entry = "sfe_replay_sequence";
   if (pair_stride < 1 || nframes < 0) return rfail(ctx, SFE_ERR_INVALID, "bad sequence arguments", cudaSuccess);
   if (nframes <= pair_stride) return SFE_SUCCESS;   // no pair
   return replay_run(ctx, w, h, depth, nframes - pair_stride, pair_stride, frames_bgr, nullptr, row_stride, frame_stride, n_per_pair,
                     from_xy, to_xy, levels, default_levels, thr, maxit, fb_max, back_xy, status_fwd, status_bwd, accepted, steps,
                     chunk_pairs);
+}
+
+extern "C" int sfe_replay_sequence_yuyv(sfe_ctx* ctx, int w, int h, int depth, int nframes, int pair_stride,
+                                        const uint8_t* frames_yuyv, size_t row_stride, size_t frame_stride, int n_per_pair,
+                                        const float* from_xy, float* to_xy, const int32_t* levels, int default_levels,
+                                        float thr, int maxit, double fb_max, float* back_xy, int32_t* status_fwd,
+                                        int32_t* status_bwd, uint8_t* accepted, int32_t* steps, int chunk_pairs) {
+  if (!ctx) return SFE_ERR_INVALID;
+  g_entry = "sfe_replay_sequence_yuyv";
+  if (pair_stride < 1 || nframes < 0) return rfail(ctx, SFE_ERR_INVALID, "bad sequence arguments", cudaSuccess);
+  if (nframes <= pair_stride) return SFE_SUCCESS;   // no pair
+  return replay_run(ctx, w, h, depth, nframes - pair_stride, pair_stride, frames_yuyv, nullptr, row_stride, frame_stride, n_per_pair,
+                    from_xy, to_xy, levels, default_levels, thr, maxit, fb_max, back_xy, status_fwd, status_bwd, accepted, steps,
+                    chunk_pairs, true);
 }

@@ -98,7 +98,7 @@ struct TrackArgs {
   int default_levels;
   float thr;
   int maxit;
-  float fb_max;
+  double fb_max;  // matcher.cpp:201 compares a double norm with the double literal 0.3
   float* back_xy;
   int32_t* status_fwd;
   int32_t* status_bwd;

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
     const int ff = a.from_first + pair, tf = a.to_first + pair;
     const float fx = a.from_xy[2 * i], fy = a.from_xy[2 * i + 1];
     float tx = a.to_xy[2 * i], ty = a.to_xy[2 * i + 1];
-    const int lv = a.levels ? a.levels[i] : a.default_levels;
+    const int lv = max(1, a.levels ? a.levels[i] : a.default_levels);  // a level count < 1 is tracked as 1 (host entries reject it)
     int steps = 0;
     int st[2];
     TileTag tag{nullptr, 0u};
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS, TRK_MINB) track_fb_kernel(PyrV
     if (ok && a.ndir == 2) {
       float ddx = fx - bx, ddy = fy - by;
       double nrm = sqrt(__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)));
-      if (nrm > (double)a.fb_max) ok = false;  // matcher.cpp:201
+      if (nrm > a.fb_max) ok = false;  // matcher.cpp:201
     }
     if (lane == 0) {
       a.to_xy[2 * i] = tx;

@@ -165,7 +165,7 @@ class GpuTracker {
   };
   FBResult TrackFeaturesFB(const Pyramid& from, const Pyramid& to, const std::vector<Point2f>& from_pt,
                            const std::vector<Point2f>& seed, const std::vector<int32_t>& levels, float threshold = 0.001f,
-                           int max_iterations = 10, float fb_max = 0.3f) const {
+                           int max_iterations = 10, double fb_max = 0.3) const {
     const int n = (int)from_pt.size();
     if ((int)seed.size() != n || (!levels.empty() && (int)levels.size() != n)) throw Error("TrackFeaturesFB: size mismatch");
     FBResult r;

@@ -27,7 +27,10 @@ struct BgrImage {
 
 namespace png_detail {
 
-// ---- RFC 1951 inflate (stored, fixed and dynamic Huffman blocks)
+// ---- RFC 1951 inflate (stored, fixed and dynamic Huffman blocks).  The canonical-Huffman decoder (per-length code
+// counts plus a symbol table, decoded bit by bit against a running first/index pair) is the scheme of Mark Adler's
+// public-domain "puff" reference inflater (zlib contrib/puff), restated for this header.  `limit` bounds the output:
+// replay directories are external input, and a small file must not inflate without bound.
 struct BitReader {
   const uint8_t* p;
   size_t n, pos = 0;
@@ -80,7 +83,7 @@ struct Huffman {
   }
 };
 
-inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t limit) {
   static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   static const uint16_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
   static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -95,7 +98,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
       if (br.pos + 4 > n) return false;
       const unsigned len = src[br.pos] | (src[br.pos + 1] << 8), nlen = src[br.pos + 2] | (src[br.pos + 3] << 8);
       br.pos += 4;
-      if ((len ^ 0xffffu) != nlen || br.pos + len > n) return false;
+      if ((len ^ 0xffffu) != nlen || br.pos + len > n || out.size() + len > limit) return false;
       out.insert(out.end(), src + br.pos, src + br.pos + len);
       br.pos += len;
     } else if (type == 1 || type == 2) {
@@ -136,8 +139,10 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
       for (;;) {
         int sym = hl.decode(br);
         if (sym < 0) return false;
-        if (sym < 256) out.push_back((uint8_t)sym);
-        else if (sym == 256) break;
+        if (sym < 256) {
+          if (out.size() >= limit) return false;
+          out.push_back((uint8_t)sym);
+        } else if (sym == 256) break;
         else {
           sym -= 257;
           if (sym >= 29) return false;
@@ -145,7 +150,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
           const int ds = hd.decode(br);
           if (ds < 0 || ds >= 30) return false;
           const size_t dist = dbase[ds] + (size_t)br.bits(dext[ds]);
-          if (!br.ok || dist > out.size()) return false;
+          if (!br.ok || dist > out.size() || out.size() + (size_t)len > limit) return false;
           size_t from = out.size() - dist;
           for (int k = 0; k < len; ++k) out.push_back(out[from + k]);
         }
@@ -192,8 +197,12 @@ inline bool DecodePng(const uint8_t* file, size_t n, BgrImage* img) {
   switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: return false; }
   if (depth != 8 || interlace != 0 || w == 0 || h == 0 || w > 32768 || h > 32768 || idat.size() < 6) return false;
   std::vector<uint8_t> raw;
-  raw.reserve((size_t)h * ((size_t)w * ch + 1));
-  if (!inflate(idat.data() + 2, idat.size() - 2, raw)) return false;  // skip the 2-byte zlib header; Adler-32 not checked
+  // the decoded size is known from IHDR; deflate expands at most 1032x, so a header that promises more than the
+  // IDAT bytes can hold is rejected before anything is allocated, and inflate() stops at the expected size
+  const size_t expected = (size_t)h * ((size_t)w * ch + 1);
+  if (expected > idat.size() * 1032 + 1024) return false;
+  raw.reserve(expected);
+  if (!inflate(idat.data() + 2, idat.size() - 2, raw, expected)) return false;  // skip the 2-byte zlib header; Adler-32 not checked
   const size_t stride = (size_t)w * ch;
   if (raw.size() < (size_t)h * (stride + 1)) return false;
   // undo the scanline filters in place (PNG spec 9.2)

@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
     bool ok = !(s1 || s2);
     if (ok) {
       float dx = corners[i].x - back_pt.x, dy = corners[i].y - back_pt.y;
-      if (std::sqrt((double)dx * dx + (double)dy * dy) > (double)0.3f) ok = false;
+      if (std::sqrt((double)dx * dx + (double)dy * dy) > 0.3) ok = false;  // matcher.cpp:201
     }
     if (ok != (bool)fb.accepted[i] || to_pt.x != fb.to_pt[i].x || to_pt.y != fb.to_pt[i].y || s1 != fb.status_fwd[i]) ++mismatches;
     if (p1.size() != 3 || p1[0].data.size() != 169 || p1[0].size.width != 13) ++mismatches;

@@ -52,3 +52,22 @@ def test_sharded_matcher_gloo_world2(tmp_path, nq, nt):
     port = 29500 + (os.getpid() % 2000) + nq % 7
     mp.spawn(_worker, args=(2, port, nq, nt, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_c_abi_shard_range_matches_host_layer(sfe):
+    """sfe_shard_range (the C ABI's block rule, pure host arithmetic: callable without a GPU) == dist.shard_range, and
+    the blocks tile [0, n) in rank order -- which is what makes an in-place all-gather of the rows correct."""
+    import ctypes
+    sd = importlib.import_module("slam-robot_b200.dist")
+    L = sfe.lib()
+    for n in (0, 1, 7, 8, 65536, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            end = 0
+            for r in range(world):
+                lo, hi = ctypes.c_int64(), ctypes.c_int64()
+                assert L.sfe_shard_range(n, r, world, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                assert (lo.value, hi.value) == sd.shard_range(n, r, world) and lo.value == end
+                end = hi.value
+            assert end == n
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    assert L.sfe_shard_range(5, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) != 0   # rank out of range

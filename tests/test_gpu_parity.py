@@ -275,6 +275,33 @@ def test_config2_measured_shape_bit_exact(fe, po, sfe, synth):
         assert o["accepted"].sum() > 0.5 * NFEAT
 
 
+def test_replay_sequence_yuyv_equals_bgr_replay(fe, po, synth):
+    """sfe_replay_sequence_yuyv: frames in the camera's native packed YUYV (2 bytes per pixel over PCIe), converted on
+    the device with video.cpp:187-223's integer arithmetic, equal sfe_replay_sequence on the BGR frames that loop
+    produces (oracle conversion), bit for bit."""
+    H, W, S = 240, 320, 2
+    rng = np.random.default_rng(9)
+    A, B = synth.make_pairs(33, 4, H, W)
+    bgr = np.concatenate([A.numpy(), B.numpy()])[[0, 1, 4, 5, 2, 3, 6, 7]]        # stride-2 pairs (0,4)->(0,2) etc.
+    # a YUYV sequence whose luma follows the synthetic frames (chroma random): what matters is that both paths see
+    # the BGR bytes video.cpp's loop makes of it
+    yuyv = np.empty((len(bgr), H, W, 2), np.uint8)
+    yuyv[..., 0] = bgr[..., 1]
+    yuyv[..., 1] = rng.integers(96, 160, (len(bgr), H, W), dtype=np.uint8)
+    conv = np.stack([po.yuyv_to_bgr(f.reshape(-1)).reshape(H, W, 3) for f in yuyv])
+    npairs, npp = len(bgr) - S, 120
+    pts = np.concatenate([synth.make_features(60 + p, npp, H, W, margin=16) for p in range(npairs)])
+    a = fe.replay_sequence(np.ascontiguousarray(conv), S, pts, pts, 4, 3, n_per_pair=npp, chunk_pairs=4)
+    b = fe.replay_sequence(yuyv, S, pts, pts, 4, 3, n_per_pair=npp, chunk_pairs=4)
+    for k in ("status_fwd", "status_bwd", "accepted", "steps"):
+        assert np.array_equal(a[k], b[k]), k
+    assert_bits_equal(a["to_xy"], b["to_xy"], "to_xy")
+    assert_bits_equal(a["back_xy"], b["back_xy"], "back_xy")
+    o = po.hes_track_fb(po.Pyramid(conv[1], 4), po.Pyramid(conv[3], 4), pts[npp:2 * npp], pts[npp:2 * npp], 3)
+    assert_bits_equal(b["to_xy"][npp:2 * npp], o["to_xy"], "pair 1 vs oracle")
+    assert np.array_equal(b["accepted"][npp:2 * npp], o["accepted"])
+
+
 @pytest.mark.parametrize("chunk", [2, 0, 5])
 def test_replay_pairs_pipeline_matches_oracle(fe, po, synth, chunk):
     """sfe_replay_pairs (host buffers, chunk-pipelined: copy | pyramid (three sets) | tracking | download streams):

@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
   std::vector<int32_t> s1(n), s2(n);
   std::vector<uint8_t> acc(n);
   CHECK(sfe_replay_sequence(ctx, w, h, 6, nframes, 2, frames.data(), (size_t)3 * w, (size_t)3 * w * h, max_corners, from_xy.data(),
-                            to_xy.data(), nullptr, 3, 0.001f, 10, 0.3f, back.data(), s1.data(), s2.data(), acc.data(), nullptr, 0));
+                            to_xy.data(), nullptr, 3, 0.001f, 10, 0.3, back.data(), s1.data(), s2.data(), acc.data(), nullptr, 0));
   FILE* out = argc > 3 ? fopen(argv[3], "w") : nullptr;
   for (int p = 0; p < npairs; ++p) {
     int m = 0;
