@@ -1,18 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the front-end hot path on synthetic frames (BASELINE.json metric).
 
-One STEP = one batch of B independent 640x480 frame pairs through the whole path:
+One STEP = one batch of B independent 640x480 frame pairs through the whole path (BASELINE config 2):
   MakePyramid of both frames (hessian.h flavour, 4 levels)            -> pyr_* kernels
   forward/backward patch tracking of 2000 features per pair (P1)      -> track_fb_kernel
   2000 x 2000 256-bit Hamming top-2 + ratio test per pair (P4)        -> hamming_* kernels
-`value` is frame pairs/s with all inputs resident in HBM; `e2e` is the same metric through the
-host-pointer C ABI (pinned host buffers, H2D/D2H inside the timed region).
+`value` is frame pairs/s with all inputs resident in HBM.  `e2e` is the same metric through the host-pointer C ABI
+(pinned host buffers, H2D/D2H inside the timed region): the B pairs arrive as a replayed alternating-camera sequence
+of B + 2 frames (sfe_replay_sequence: pair i = frames i, i + 2; every frame crosses PCIe and is built once, as
+Matcher::Track builds one pyramid per new frame, matcher.cpp:317) plus the descriptor sets of the step.
+Before anything is printed, pair 0 of both paths is compared with the CPU oracle (a mismatch is a non-zero exit).
+
+`other_configs` carries the remaining BASELINE configurations, measured in the same run: C1 (one frame, 500 features,
+host-pointer ABI: latency), C3 (1920x1080, 5000 features, 8 levels), C4 (this rank's shard of a 65,536-pair replay
+through sfe_replay_sequence; a few calls are timed and the shard is projected) and C5 (1M x 1M descriptors, query rows
+sharded over the ranks, train set broadcast and result rows all-gathered with NCCL inside libslamfe: strong scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
-For N > 1 launch with torch.distributed.run (one rank per GPU, weak scaling: every rank
-processes its own B pairs; the path has no data-path collective).
+For N > 1 launch with torch.distributed.run (one rank per GPU, weak scaling: every rank processes its own B pairs;
+the tracking path has no data-path collective; C5 is the one exchange).
 """
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -30,32 +39,32 @@ if ROOT not in sys.path:
 W, H, NFEAT, LEVELS, DEPTH = 640, 480, 2000, 4, 4
 THR, MAXIT, FB_MAX = 0.001, 10, 0.3
 RATIO = (4, 5, 80)
+SEQ_STRIDE = 2
 WORKLOAD = "C2: 640x480 frame pairs, 2000 features/pair, 4-level pyramid (both frames) + forward/backward " \
            "Hessian patch tracking + 2000x2000 256-bit Hamming top-2"
+METRIC = "tracked frame pairs/sec (pyramid + fwd/bwd track + Hamming match)"
+# identical in both arms (the driver compares the dicts): the per-pair workload; batch sizes are reported beside it
+CONFIG = {"workload": WORKLOAD, "width": W, "height": H, "features": NFEAT, "levels": LEVELS,
+          "l2": "inputs larger than L2 on the GPU arm (hundreds of MB of BGR frames and pyramids per step)"}
 
 
-def measured_traffic(kernel, batch):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic_r1.json), only when the
-    capture was taken at this batch size; None otherwise."""
+def tracker_source_hash():
+    """Identifies the build the ncu calibration in profiles/ belongs to: the tracker's sources and build flags."""
+    h = hashlib.sha256()
+    for f in ("track_hessian.cu", "patch.cuh", "sfe_common.cuh", "build.sh"):
+        with open(os.path.join(ROOT, "slam-robot_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def calibration():
+    """profiles/traffic.json: per-launch DRAM bytes and warp-instructions per Newton step of the tracking kernel from
+    the committed ncu capture, valid only for the build whose source hash it records (tools/ncu_calibrate.py)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            e = json.load(f)[kernel]
-        return float(e["dram_bytes"]) if int(e["batch_pairs"]) == int(batch) else None
-    except Exception:
-        return None
-
-
-def issue_fraction(newton_steps, trk_ms, sms, clocks):
-    """Issue-slot utilisation of the tracking kernel: warp-instructions per second against 4 schedulers per SM x SM clock."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            per_step = float(json.load(f)["track_fb_kernel"]["ncu_warp_instructions_per_newton_step"])
-        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
-        achieved = per_step * newton_steps / (trk_ms * 1e-3)
-        peak = sms * 4 * mhz * 1e6
-        return {"bound": "instruction issue", "achieved": achieved, "peak": peak, "unit": "warp-instructions/s",
-                "frac": achieved / peak, "warp_instructions_per_newton_step": per_step,
-                "source": "profiles/track_r1i_summary.txt (ncu) x Newton steps counted by the kernel in this run"}
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            c = json.load(f)
+        c["stale"] = c.get("tracker_source_hash") != tracker_source_hash()
+        return c
     except Exception:
         return None
 
@@ -157,6 +166,24 @@ def make_inputs(torch, synth, batch, device, seed):
     return A, B, pts.astype(np.float32), q, t
 
 
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def oracle_check_pair(po, frame_a, frame_b, pts, got, sl, what):
+    """One pair of a step against the CPU oracle: positions bit for bit, statuses, accept flags, Newton steps."""
+    oa, ob = po.Pyramid(frame_a, DEPTH), po.Pyramid(frame_b, DEPTH)
+    o = po.hes_track_fb(oa, ob, pts, pts, LEVELS, THR, MAXIT, FB_MAX)
+    bad = [k for k in ("to_xy", "back_xy") if not same_bits(got[k][sl], o[k])]
+    bad += [k for k in ("status_fwd", "status_bwd", "accepted") if not np.array_equal(got[k][sl], o[k])]
+    if int(np.asarray(got["steps"][sl]).sum()) != o["newton_steps"]:
+        bad.append("steps")
+    if bad:
+        raise SystemExit("bench.py: %s differs from the CPU oracle in %s -- refusing to print a number" % (what, bad))
+    return int(o["accepted"].sum())
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -177,6 +204,18 @@ def run_gpu(args):
     fe = sfe.FrontEnd(local)
     stream = torch.cuda.Stream(device=dev)
     fe.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(vals):
+        tt = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tt]
 
     A, Bf, pts, q, t = make_inputs(torch, synth, B, dev, seed=1 + rank)
     n = B * NFEAT
@@ -204,12 +243,6 @@ def run_gpu(args):
         if ev: ev[2].record(stream)
         fe.match_hamming256(q_d, t_d, *RATIO, batch=B, out=ham_out)
         if ev: ev[3].record(stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
         # clocks / throttle reasons are sampled from the first warm-up step through the timed region and an
@@ -246,10 +279,32 @@ def run_gpu(args):
     accepted = int(trk_out["accepted"].sum().item())
     passed = int(ham_out[2].sum().item())
 
-    # ---- end to end through the host-pointer C ABI (the call a user makes): pinned host inputs, results back
-    # in host memory.  sfe_replay_pairs pipelines the step in chunks (upload | pyramids + tracking | download);
-    # the descriptor matching of the step is enqueued first with sfe_match_hamming256_async and drains with it.
-    hA, hB = frames[:B].cpu().pin_memory(), frames[B:].cpu().pin_memory()
+    # ---- parity gate on the measured step itself: pair 0 and pair B-1 of this rank's last step against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_check:
+        from oracle import pyoracle as po
+        host = {k: v.cpu().numpy() for k, v in trk_out.items()}
+        host["to_xy"] = to_xy.cpu().numpy()
+        hi, hd, hp = (v.cpu().numpy() for v in ham_out)
+        checked = []
+        for p in sorted({0, B - 1}):
+            sl = slice(p * NFEAT, (p + 1) * NFEAT)
+            oracle_check_pair(po, frames[p].cpu().numpy(), frames[B + p].cpu().numpy(), pts[sl], host, sl, "resident step, pair %d" % p)
+            oi, od, oo = po.hamming256_top2(q[sl], t[sl], *RATIO)
+            if not (np.array_equal(hi[sl], oi) and np.array_equal(hd[sl], od) and np.array_equal(hp[sl], oo)):
+                raise SystemExit("bench.py: Hamming top-2 of pair %d differs from the CPU oracle" % p)
+            checked.append(p)
+        parity = {"resident_pairs_checked": checked, "outputs": "pyramid-dependent tracks (positions bit for bit, statuses, accept "
+                  "flags, Newton steps) and Hamming idx/dist/pass of those pairs == CPU oracle"}
+
+    # ---- end to end through the host-pointer C ABI (the call a user makes): pinned host inputs, results back in host
+    # memory.  The B pairs of a step arrive as a replayed alternating-camera SEQUENCE of B + 2 frames
+    # (sfe_replay_sequence: every frame is uploaded and built once); the descriptor matching of the step is enqueued first
+    # with sfe_match_hamming256_async and drains with it.
+    del frames, pyr
+    torch.cuda.empty_cache()
+    nfr = B + SEQ_STRIDE
+    seq = synth.make_sequence(77 + rank, nfr, H, W, stride=SEQ_STRIDE, device=dev).cpu().pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
     fe.set_stream(None)
     h_pts = fe.pinned((n, 2), np.float32)
@@ -260,11 +315,12 @@ def run_gpu(args):
     h_trk = dict(to_xy=fe.pinned((n, 2), np.float32), back_xy=fe.pinned((n, 2), np.float32), status_fwd=fe.pinned((n,), np.int32),
                  status_bwd=fe.pinned((n,), np.int32), accepted=fe.pinned((n,), np.uint8), steps=fe.pinned((n,), np.int32))
     h_ham = (fe.pinned((n, 2), np.int32), fe.pinned((n, 2), np.int32), fe.pinned((n,), np.uint8))
+    chunk = int(os.environ.get("SFE_BENCH_CHUNK", "0"))
 
     def step_e2e():
         fe.match_hamming256_async(h_q, h_t, h_ham, *RATIO, batch=B)
-        r = fe.replay_pairs(hA, hB, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk,
-                            chunk_pairs=int(os.environ.get("SFE_BENCH_CHUNK", "0")))
+        r = fe.replay_sequence(seq, SEQ_STRIDE, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk,
+                               chunk_pairs=chunk)
         fe.sync()  # joins the matcher's side stream: every result of the step is in host memory when the step ends
         return r, h_ham
 
@@ -275,33 +331,44 @@ def run_gpu(args):
         r, m = step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = 2 * B * H * W * 3 + n * 16 + 2 * n * 32
+    h2d = nfr * H * W * 3 + n * 16 + 2 * n * 32
     d2h = n * (8 + 8 + 4 + 4 + 1 + 4) + n * (8 + 8 + 1)
-    assert np.array_equal(r["accepted"], trk_out["accepted"].cpu().numpy()), "host and device paths disagree"
-    assert np.array_equal(m[0], ham_out[0].cpu().numpy()), "host and device matching paths disagree"
+    if not np.array_equal(m[0], hi if parity else ham_out[0].cpu().numpy()):
+        raise SystemExit("bench.py: host and device matching paths disagree")
+    if parity is not None:
+        from oracle import pyoracle as po
+        sq = seq.numpy()
+        for p in sorted({0, B - 1}):
+            sl = slice(p * NFEAT, (p + 1) * NFEAT)
+            oracle_check_pair(po, sq[p], sq[p + SEQ_STRIDE], pts[sl], r, sl, "end-to-end step, pair %d" % p)
+        parity["e2e_pairs_checked"] = sorted({0, B - 1})
+    e2e_accept = float(np.mean(r["accepted"]))
 
-    # ---- max over ranks
-    tt = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(tt[0]), float(tt[1])
+    ms_total, e2e_ms = max_over_ranks([ms_total, e2e_s * 1e3])
+    other = other_configs(args, torch, dist, sfe, synth, fe, dev, rank, world, seq, h_pts, h_trk, max_over_ranks, barrier)
 
     if rank == 0:
         peak, peak_src = peaks()
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
-        pyr_bytes = 2 * B * pyr.bytes_per_frame()                      # per step, both pyramids of every pair
+        pyr_bytes = 2 * B * (3 * W * H + 4 * sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(DEPTH)))
         trk_bytes = pyr_bytes - 2 * B * 3 * W * H + n * 45            # read both pyramids once + 45 B/feature
         trk_ms = ms_trk / args.steps
         pyr_ms = ms_pyr / args.steps
         ham_ms = ms_ham / args.steps
+        cal = calibration()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        issue_peak = sms * 4 * mhz * 1e6
+        usable = cal is not None and not cal["stale"] and int(cal.get("batch_pairs", -1)) == B
+        per_step = float(cal["track_fb_kernel"]["warp_instructions_per_newton_step"]) if usable else None
+        issue_achieved = per_step * newton / (trk_ms * 1e-3) if usable else None
+        e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
         line = {
-            "metric": "tracked frame pairs/sec (pyramid + fwd/bwd track + Hamming match)", "value": value,
+            "metric": METRIC, "value": value,
             "unit": "frame pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_pairs_per_gpu": B, "width": W, "height": H, "features": NFEAT,
-                       "levels": LEVELS, "l2": "inputs larger than L2 (%.0f MB BGR + %.0f MB pyramids per step)" % (
-                           2 * B * H * W * 3 / 1e6, 2 * B * 4 * sum((W >> l) * (H >> l) for l in range(DEPTH)) / 1e6)},
+            "config": CONFIG, "batch_pairs_per_gpu": B,
             "features_per_sec": world * n * args.steps / (ms_total * 1e-3),
             "matches_per_sec": world * n * args.steps / (ms_total * 1e-3),
             "hamming_comparisons_per_sec_kernel": B * NFEAT * NFEAT / (ham_ms * 1e-3),
@@ -309,35 +376,209 @@ def run_gpu(args):
             "phase_ms": {"pyramid": pyr_ms, "track": trk_ms, "hamming": ham_ms},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "frame pairs/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            # dominant kernel: track_fb_kernel (one launch per step). Latency/issue bound, NOT HBM bound
-            # (pyramids are read once and then live in L1/L2) -- the fraction is reported as asked.
-            "roofline": {"kernel": "track_fb_kernel<HESSIAN>", "bound": "hbm", "achieved": trk_bytes / (trk_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": trk_bytes / (trk_ms * 1e-3) / 1e9 / peak,
-                         "traffic": measured_traffic("track_fb_kernel", B), "algorithmic_bytes": trk_bytes,
-                         "peak_source": peak_src, "share_of_step": trk_ms / ms_step,
+            "parity": parity,
+            "e2e": {"value": e2e_value, "unit": "frame pairs/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "entry": "sfe_match_hamming256_async + sfe_replay_sequence (stride %d: %d frames = %d pairs per step) + sfe_sync" % (
+                        SEQ_STRIDE, nfr, B),
+                    # what each rank's host link actually carried: tells a PCIe limit from a host-DRAM limit as N grows
+                    "h2d_gbs_per_rank": h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                    "accepted_frac": e2e_accept},
+            # dominant kernel: track_fb_kernel (one launch per step).  It is bound by instruction issue, not by HBM: a
+            # pyramid pair is read once (DRAM traffic ~ the algorithmic bytes, <1 % of the HBM peak) and then lives in
+            # L1/L2.  achieved = executed warp-instructions per Newton step (ncu capture of THIS build,
+            # profiles/traffic.json, refused when the tracker's source hash differs) x Newton steps counted live by the
+            # kernel / its CUDA-event time; peak = 4 schedulers x SMs x the SM clock sampled in this run.
+            "roofline": {"kernel": "track_fb_kernel<HESSIAN>", "bound": "issue", "achieved": issue_achieved, "peak": issue_peak,
+                         "unit": "warp-instructions/s", "frac": issue_achieved / issue_peak if usable else None,
+                         "traffic": float(cal["track_fb_kernel"]["dram_bytes"]) if usable else None,
+                         "warp_instructions_per_newton_step": per_step,
+                         "calibration": None if cal is None else {"file": "profiles/traffic.json", "stale": bool(cal["stale"]),
+                                                                  "batch_pairs": cal.get("batch_pairs")},
+                         "share_of_step": trk_ms / ms_step,
+                         "newton_steps_per_sec": newton / (trk_ms * 1e-3),
                          "bilinear_samples_per_sec": (newton * 6 * 169) / (trk_ms * 1e-3),
-                         # what actually bounds it: instruction issue.  Executed warp-instructions per Newton step come
-                         # from the committed ncu capture of this kernel, the Newton steps are counted live by the kernel.
-                         "issue": issue_fraction(newton, trk_ms, torch.cuda.get_device_properties(dev).multi_processor_count,
-                                                 clocks)},
+                         "hbm": {"algorithmic_bytes": trk_bytes, "achieved": trk_bytes / (trk_ms * 1e-3) / 1e9, "peak": peak,
+                                 "unit": "GB/s", "frac": trk_bytes / (trk_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src}},
             # the HBM-streaming kernels of the path
             "roofline_pyramid": {"kernel": "pyr_row_kernel (levels 0+1 fused) + pyr_stream_kernel<down> x2, one build of 2B frames",
                                  "bound": "hbm",
                                  "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak, "traffic": measured_traffic("pyramid_build", B),
-                                 "algorithmic_bytes": pyr_bytes,
-                                 "note": "write-bound: the build writes 1.6x what it reads; write-only HBM traffic reaches 3.9 TB/s and a "
-                                         "5 read : 8 write mix 5.5 TB/s on this GPU (tools/hbm_mix_probe.py), against 6.5 TB/s for the copy "
-                                         "that defines `peak`",
+                                 "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peak,
+                                 "traffic": float(cal["pyramid_build"]["dram_bytes"]) if usable and "pyramid_build" in cal else None,
+                                 "algorithmic_bytes": pyr_bytes, "peak_source": peak_src,
                                  "share_of_step": pyr_ms / ms_step},
+            "other_configs": other,
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(sample_pairs=args.cpu_pairs)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(args, torch, dist, sfe, synth, fe, dev, rank, world, seq, h_pts, h_trk, max_over_ranks, barrier):
+    """BASELINE configs 1, 3, 4, 5 under the same clock (each a short measurement; the details say how short)."""
+    if args.no_other:
+        return None
+    out = {}
+    B = args.batch
+    # ---- C4: this rank's shard of a 65,536-pair replay through sfe_replay_sequence (host buffers, pipelined)
+    total_pairs = 65536
+    lo, hi = importlib.import_module("slam-robot_b200.dist").shard_range(total_pairs, rank, world)
+    calls = 3
+    fe.replay_sequence(seq, SEQ_STRIDE, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        fe.replay_sequence(seq, SEQ_STRIDE, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+    torch.cuda.synchronize()
+    (c4_s,) = max_over_ranks([time.perf_counter() - t0])
+    rate = world * B * calls / c4_s
+    out["C4_replay_65536_pairs"] = {
+        "pairs_per_sec": rate, "unit": "frame pairs/s (pyramid + fwd/bwd track, end to end from pinned host memory)",
+        "shard_pairs_per_rank": hi - lo, "timed": "%d calls of sfe_replay_sequence x %d pairs per rank (%.1f %% of the shard), "
+        "max over ranks; no data-path collective" % (calls, B, 100.0 * calls * B / max(hi - lo, 1)),
+        "projected_seconds_for_65536_pairs": total_pairs / rate}
+
+    # ---- C5: 1M x 1M descriptors, strong scaling: query rows sharded, train broadcast + rows all-gathered by NCCL
+    # inside libslamfe (sfe_match_hamming256_sharded_dev); all collectives and kernels on one stream, CUDA-event timed
+    nq = nt = args.c5_n
+    stream = torch.cuda.Stream(device=dev)
+    fe.set_stream(stream.cuda_stream)
+
+    def exchange(id128):
+        tns = torch.from_numpy(id128).to(dev)
+        dist.broadcast(tns, 0)
+        return tns.cpu().numpy()
+
+    fe.dist_init(rank, world, exchange=exchange)
+    t_np = synth.make_descriptors(11, nt, dup_frac=0.001)
+    q_np = synth.make_descriptors(12, nq, dup_frac=0.01, source=t_np)
+    qlo, qhi = fe.shard_range(nq)
+    with torch.cuda.stream(stream):
+        q_loc = torch.from_numpy(q_np[qlo:qhi].view(np.int32)).to(dev)
+        t_root = torch.from_numpy(t_np.view(np.int32)).to(dev) if rank == 0 else None
+        t_buf = torch.empty((nt, 8), dtype=torch.int32, device=dev)
+        res = (torch.empty((nq, 2), dtype=torch.int32, device=dev), torch.empty((nq, 2), dtype=torch.int32, device=dev),
+               torch.empty(nq, dtype=torch.uint8, device=dev))
+        ms = []
+        for it in range(2):   # the first pass warms NCCL's channels up
+            if rank == 0:
+                t_buf.copy_(t_root)
+            else:
+                t_buf.zero_()   # the train set must really arrive through the broadcast
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fe.match_hamming256_sharded(q_loc, nq, t_buf, nt, 0, *RATIO, out=res)
+            e1.record(stream)
+            barrier()
+            ms.append(e0.elapsed_time(e1))
+        (c5_ms,) = max_over_ranks([ms[-1]])
+        # identical results on every rank: a checksum of the gathered arrays, compared across ranks
+        chk = (res[0].to(torch.int64) * 1000003 + res[1].to(torch.int64)).sum() + res[2].to(torch.int64).sum() * 7
+        chks = [torch.zeros_like(chk) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(chks, chk)
+        else:
+            chks = [chk]
+        same = all(int(c) == int(chks[0]) for c in chks)
+        if not same:
+            raise SystemExit("bench.py: C5 gathered results differ between ranks")
+        oracle_rows = 0
+        if rank == 0 and not args.no_check:
+            from oracle import pyoracle as po
+            rows = np.r_[0:64, nq // 2:nq // 2 + 64, nq - 64:nq]   # rows of the first, a middle and the last shard
+            oi, od, oo = po.hamming256_top2(q_np[rows], t_np, *RATIO)
+            gi, gd, gp = (v[torch.from_numpy(rows).to(dev)].cpu().numpy() for v in res)
+            if not (np.array_equal(gi, oi) and np.array_equal(gd, od) and np.array_equal(gp, oo)):
+                raise SystemExit("bench.py: C5 rows differ from the CPU oracle")
+            oracle_rows = len(rows)
+    fe.dist_shutdown()
+    fe.set_stream(None)
+    out["C5_hamming_1Mx1M"] = {
+        "seconds": c5_ms * 1e-3, "comparisons_per_sec": nq * nt / (c5_ms * 1e-3), "nq": nq, "nt": nt, "scaling": "strong",
+        "ranks": world, "collectives": "ncclBroadcast(train, %d MB) + sharded match + in-place ncclAllGather(idx, dist, pass: %d MB), "
+        "issued by libslamfe on the kernels' stream; CUDA events, max over ranks" % (nt * 32 >> 20, nq * 17 >> 20),
+        "results_identical_across_ranks": same, "oracle_rows_checked": oracle_rows}
+    del q_loc, t_buf, res, t_root
+    torch.cuda.empty_cache()
+
+    if rank != 0:   # C1 and C3 are single-GPU shapes ("replicas only"): rank 0 measures them while the others wait
+        barrier()
+        return out
+
+    # ---- C1: the live robot's shape -- ONE 640x480 frame, 500 features, host-pointer ABI (frame upload + 6-level
+    # pyramid + forward/backward tracking at 3 levels + results back), and the keyframe's corner seeding
+    A1, B1 = synth.make_pairs(5, 1, H, W)
+    A1, B1 = A1.numpy(), B1.numpy()
+    p1 = synth.make_features(9, 500, H, W, margin=16.0).astype(np.float32)
+    hA, hB = fe.pinned(A1.shape, np.uint8), fe.pinned(B1.shape, np.uint8)
+    hA[...] = A1
+    hB[...] = B1
+    pa, pb = fe.pyramid(W, H, 6, sfe.HESSIAN, 1), fe.pyramid(W, H, 6, sfe.HESSIAN, 1)
+    pa.build(hA)
+    c1 = {}
+    for levels in (3, 6):
+        def frame():
+            pb.build(hB)                                   # the new frame's pyramid (host pointer: H2D inside)
+            return fe.track_fb(pa, pb, p1, p1.copy(), levels, THR, MAXIT, FB_MAX, n_per_pair=500)
+        for _ in range(5):
+            frame()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            r1 = frame()
+        c1["us_per_frame_%d_levels" % levels] = (time.perf_counter() - t0) / 50 * 1e6
+    for _ in range(3):
+        fe.good_features(hB[0], 120, 0.01, 20.0)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        corners = fe.good_features(hB[0], 120, 0.01, 20.0)
+    c1["us_corner_seeding_120"] = (time.perf_counter() - t0) / 20 * 1e6
+    c1.update({"features": 500, "accepted_frac": float(np.mean(r1["accepted"])), "corners": int(len(corners[0])),
+               "what": "wall clock per call through the host-pointer C ABI from Python (50 / 20 repetitions), one B200"})
+    out["C1_one_frame_500_features"] = c1
+    pa.close()
+    pb.close()
+
+    # ---- C3: 1920x1080, 5000 features per frame, 8-level pyramid; a step = 16 pairs (32 pyramids + tracking), resident
+    W3, H3, NF3, D3, B3 = 1920, 1080, 5000, 8, 16
+    stream = torch.cuda.Stream(device=dev)
+    fe.set_stream(stream.cuda_stream)
+    a3, b3 = synth.make_pairs(100, B3, H3, W3, device=dev)
+    fr3 = torch.cat([a3, b3]).contiguous()
+    del a3, b3
+    pts3 = np.concatenate([synth.make_features(7 + p, NF3, H3, W3, margin=16.0) for p in range(B3)]).astype(np.float32)
+    f3 = torch.from_numpy(pts3).to(dev)
+    t3 = f3.clone()
+    pyr3 = fe.pyramid(W3, H3, D3, sfe.HESSIAN, 2 * B3)
+    with torch.cuda.stream(stream):
+        def step3():
+            pyr3.build(fr3)
+            t3.copy_(f3)
+            return fe.track_fb(pyr3, pyr3, f3, t3, D3, THR, MAXIT, FB_MAX, n_per_pair=NF3, from_first=0, to_first=B3)
+        for _ in range(2):
+            r3 = step3()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream)
+        pyr3.build(fr3)
+        e[1].record(stream)
+        for _ in range(3):
+            r3 = step3()
+        e[2].record(stream)
+        torch.cuda.synchronize()
+    ms_p3, ms3 = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]) / 3
+    peak, _ = peaks()
+    out["C3_1080p_5000_features_8_levels"] = {
+        "pairs_per_sec": B3 / (ms3 * 1e-3), "features_per_sec": B3 * NF3 / (ms3 * 1e-3), "ms_per_step": ms3, "pairs_per_step": B3,
+        "pyramid_ms": ms_p3, "pyramid_hbm_frac": 2 * B3 * pyr3.bytes_per_frame() / (ms_p3 * 1e-3) / 1e9 / peak,
+        "newton_steps_per_feature": float(r3["steps"].sum().item()) / (B3 * NF3),
+        "accepted_frac": float(r3["accepted"].float().mean().item()), "what": "inputs resident, CUDA events, 3 steps, one B200"}
+    fe.set_stream(None)
+    pyr3.close()
+    barrier()
+    return out
 
 
 def host_threads():
@@ -369,6 +610,13 @@ def cpu_inputs(pairs, seed=1):
     return A.numpy(), B.numpy(), pts, q, t
 
 
+def single_thread_rate(po, A, B, pts, q, t):
+    """What the reference itself does: its front-end is single-threaded."""
+    t1 = time.perf_counter()
+    cpu_step(po, A[:1], B[:1], pts[:NFEAT], q[:NFEAT], t[:NFEAT], nthreads=1)
+    return 1.0 / (time.perf_counter() - t1)
+
+
 def cpu_baseline(sample_pairs=4):
     """Oracle port (kind "port": the reference itself cannot be built here) with the
     reference's own compiler flags, on a bounded sample of the same workload."""
@@ -380,13 +628,10 @@ def cpu_baseline(sample_pairs=4):
     t0 = time.perf_counter()
     cpu_step(po, A, B, pts, q, t)
     dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    cpu_step(po, A[:1], B[:1], pts[:NFEAT], q[:NFEAT], t[:NFEAT], nthreads=1)
-    dt1 = time.perf_counter() - t1
     return {"value": sample_pairs / dt, "unit": "frame pairs/s", "cores": cores, "kind": "port",
             "sample": "%d frame pairs of the same workload, OpenMP over features (%d threads); flags -O3 -ffast-math "
                       "-march=native (reference Makefile:4)" % (sample_pairs, cores),
-            "single_thread_value": 1.0 / dt1}
+            "single_thread_value": single_thread_rate(po, A, B, pts, q, t)}
 
 
 def run_reference(args):
@@ -406,14 +651,15 @@ def run_reference(args):
         cpu_step(po, A, B, pts, q, t)
     dt = time.perf_counter() - t0
     value = pairs * args.steps / dt
-    sample = "%d frame pairs per step on %d host threads (oracle port, -O3 -ffast-math -march=native)" % (pairs, cores)
+    sample = "%d frame pairs per step on %d host threads (oracle port, -O3 -ffast-math -march=native; the reference's own " \
+             "front-end is single-threaded: single_thread_value)" % (pairs, cores)
     print(json.dumps({
-        "impl": "reference", "metric": "tracked frame pairs/sec (pyramid + fwd/bwd track + Hamming match)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "frame pairs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "batch_pairs_per_step": pairs, "width": W, "height": H,
-                                        "features": NFEAT, "levels": LEVELS},
-        "cpu_baseline": {"value": value, "unit": "frame pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": CONFIG, "batch_pairs_per_step": pairs,
+        "cpu_baseline": {"value": value, "unit": "frame pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread_value": single_thread_rate(po, A, B, pts, q, t)},
         "e2e": {"value": value, "unit": "frame pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -425,7 +671,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frame pairs per step per GPU")
     ap.add_argument("--cpu-pairs", type=int, default=4, help="frame pairs in the bounded CPU sample")
+    ap.add_argument("--c5-n", type=int, default=1 << 20, help="query and train descriptors of the C5 phase")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block (C1, C3, C4, C5)")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle comparison of the measured step (experiments only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

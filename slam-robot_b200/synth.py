@@ -62,6 +62,30 @@ def make_pairs(seed, n, H, W, device="cpu", angle=0.004, shift=(1.7, -2.3)):
     return to_u8(A), to_u8(B)
 
 
+def make_sequence(seed, nframes, H, W, stride=2, device="cpu", angle=0.004, shift=(1.7, -2.3), period=6, noise=2.0):
+    """A replayed alternating-camera sequence as `./slam --load` reads it (main.cpp:503-519: `stride` cameras take
+    turns, so frames i and i + stride belong to the same camera).  Every camera looks at its own scene, which moves
+    back and forth: frame i shows it after m = tri(i // stride) steps of the synthetic motion (a triangle wave of
+    `period` frames, so the view never leaves the canvas margin), i.e. consecutive frames of a camera are one motion
+    step apart, forwards or backwards.  Per-frame sensor noise makes every frame unique.  uint8 (nframes, H, W, 3)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    canvas = _canvas(gen, stride, H, W, device)
+    half = period // 2
+    out = torch.empty((nframes, H, W, 3), dtype=torch.uint8, device=device)
+    for c in range(stride):
+        for m in range(half + 1):
+            idx = [i for i in range(c, nframes, stride) if half - abs((i // stride) % period - half) == m]
+            if not idx:
+                continue
+            fr = _warp_crop(canvas[c:c + 1], angle * m, (shift[0] * m, shift[1] * m), H, W)
+            for j0 in range(0, len(idx), 64):
+                sub = idx[j0:j0 + 64]
+                nz = (torch.rand((len(sub), 1, H, W), generator=gen, device=device) * 2 - 1) * noise
+                out[sub] = (fr + nz).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    return out
+
+
 def make_frames(seed, n, H, W, device="cpu"):
     """n unrelated textured frames, uint8 (n, H, W, 3)."""
     gen = torch.Generator(device=device)
