@@ -198,6 +198,12 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
                                int batch, int ratio_num, int ratio_den, int max_dist, int32_t* idx,
                                int32_t* dist, uint8_t* pass);
 
+/* Which kernel the three entries above run: 0 = chosen by problem size (default), 1 = the integer-ALU kernel
+ * (LOP3 + POPC, hamming.cu), 2 = the tensor-core kernel (exact int8 tcgen05.mma contraction, hamming_mma.cu).
+ * Both are bit-identical to the specification; the selector exists for tests and measurements.  Process-wide
+ * (also settable as SFE_HAMMING=alu|mma); an out-of-range value only queries.  Returns the previous setting. */
+int sfe_hamming_impl(int impl);
+
 /* ---- batched replay of independent frame pairs ------------------------------------------ */
 
 /* The host-side batching/stream layer: what Matcher::Track does per frame -- MakePyramid

@@ -36,7 +36,7 @@ EXPORTS = [
     "sfe_pyr_bytes_per_frame", "sfe_pyr_build", "sfe_pyr_build_dev", "sfe_pyr_download", "sfe_track_fb",
     "sfe_track_fb_dev", "sfe_track", "sfe_track_dev", "sfe_get_patches", "sfe_brute_hessian", "sfe_klt_track_fb", "sfe_klt_track_fb_dev",
     "sfe_klt_system", "sfe_brute_track", "sfe_brute_track_dev", "sfe_match_hamming256", "sfe_match_hamming256_dev",
-    "sfe_match_hamming256_async", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_replay_sequence_yuyv", "sfe_good_features",
+    "sfe_match_hamming256_async", "sfe_hamming_impl", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_replay_sequence_yuyv", "sfe_good_features",
     "sfe_good_features_dev",
     "sfe_seed_features", "sfe_seed_features_dev", "sfe_yuyv_to_bgr", "sfe_yuyv_to_bgr_dev",
     "sfe_shard_range", "sfe_dist_unique_id", "sfe_dist_init", "sfe_dist_attach", "sfe_dist_shutdown", "sfe_allgather_rows_dev",
@@ -91,6 +91,7 @@ def lib():
     L.sfe_host_alloc.argtypes = [vp, sz, vpp]
     L.sfe_host_free.argtypes = [vp, vp]
     L.sfe_launch_count.argtypes = [vp]
+    L.sfe_hamming_impl.argtypes = [i32]
     L.sfe_launch_count.restype = C.c_int64
     L.sfe_pyr_create.argtypes = [vp, i32, i32, i32, i32, i32, vpp]
     L.sfe_pyr_destroy.argtypes = [vp]
@@ -516,6 +517,11 @@ class FrontEnd:
             out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         self._chk(self.L.sfe_allgather_rows_dev(self.h, _ptr(local.contiguous()), row, int(n_total), _ptr(out)))
         return out
+
+    @staticmethod
+    def hamming_impl(impl=-1):
+        """0 = by size, 1 = integer-ALU kernel, 2 = tensor-core kernel (process-wide); returns the previous setting."""
+        return int(lib().sfe_hamming_impl(int(impl)))
 
     def match_hamming256_async(self, q, t, out, ratio_num=4, ratio_den=5, max_dist=256, batch=1):
         """Host arrays (pinned for real asynchrony); only enqueues -- call sync() before reading `out`."""

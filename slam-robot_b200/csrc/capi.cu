@@ -689,6 +689,8 @@ int sfe_match_hamming256_async(sfe_ctx* ctx, const uint32_t* q, int nq, const ui
   return SFE_SUCCESS;
 }
 
+int sfe_hamming_impl(int impl) { return hamming_set_impl(impl); }
+
 /* ---- corner seeding -------------------------------------------------- */
 
 namespace {

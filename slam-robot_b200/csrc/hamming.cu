@@ -11,6 +11,8 @@
 // tie rule, independent of the order tiles are visited, so the train set can be split over CTAs.
 // A finalize kernel merges the per-split keys, decodes them and applies the integer ratio test
 // d1 * den < d2 * num.
+#include <stdlib.h>
+
 #include "sfe_common.cuh"
 
 namespace {
@@ -111,14 +113,54 @@ __global__ void hamming_finalize_kernel(const uint2* __restrict__ keys, int nq, 
 
 }  // namespace
 
+int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int num_sms, void** ws, size_t* ws_cap,
+                       cudaStream_t s);  // hamming_mma.cu
+
+namespace {
+int device_sms() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return 148;
+  return sms;
+}
+// 0 = by size, 1 = the integer-ALU kernel, 2 = the tensor-core kernel.  Process-wide; initialised from SFE_HAMMING=alu|mma,
+// changed by sfe_hamming_impl() (tests and measurements run both kernels on the same inputs).
+int g_impl = [] {
+  const char* e = getenv("SFE_HAMMING");
+  if (!e) return 0;
+  return e[0] == 'a' ? 1 : (e[0] == 'm' ? 2 : 0);
+}();
+int forced_impl() { return g_impl; }
+}  // namespace
+
+int hamming_set_impl(int impl) {
+  const int old = g_impl;
+  if (impl >= 0 && impl <= 2) g_impl = impl;
+  return old;
+}
+
 int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int ratio_num,
                       int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass, void** ws, size_t* ws_cap, cudaStream_t s) {
   if (nq <= 0 || batch <= 0) return 0;
   if (nt > (1 << IDX_BITS)) return -(int)cudaErrorInvalidValue;
+  const int sms = device_sms();
+  const int total = batch * nq;
+  // The tensor-core kernel (hamming_mma.cu) pays a 128 x 256 tile per MMA whatever is valid in it; tiny problems stay on
+  // the ALU kernel, whose cost is proportional to the comparisons.
+  const int impl = forced_impl();
+  const bool mma = nt > 0 && (impl == 2 || (impl == 0 && (long long)total * nt >= (1ll << 22)));
+  if (mma) {
+    const int rows = launch_hamming_mma(q, nq, t, nt, batch, sms, ws, ws_cap, s);
+    if (rows < 0) return rows;
+    hamming_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>((const uint2*)*ws, nq, rows, total, ratio_num, ratio_den,
+                                                                max_dist, idx, dist, pass);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 2 : -(int)e;
+  }
   int qblocks = (nq + HM_QPB - 1) / HM_QPB;
-  // split the train set when the query tiles alone cannot fill the GPU (2 CTAs per SM target)
+  // split the train set when the query tiles alone cannot fill the GPU (4 CTAs per SM target)
   int splits = 1;
-  const int target = 148 * 4;
+  const int target = sms * 4;
   if (nt > 0 && qblocks * batch < target) splits = min((target + qblocks * batch - 1) / (qblocks * batch), (nt + HM_TT - 1) / HM_TT);
   if (splits < 1) splits = 1;
   // per-context key workspace [batch][splits][nq], grown on demand (calls are stream-ordered)
@@ -132,7 +174,6 @@ int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int 
   uint2* g_keys = (uint2*)*ws;
   dim3 grid(qblocks, splits, batch);
   hamming_kernel<<<grid, HM_THREADS, 0, s>>>((const uint4*)q, nq, (const uint4*)t, nt, splits, g_keys);
-  int total = batch * nq;
   hamming_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(g_keys, nq, splits, total, ratio_num, ratio_den,
                                                               max_dist, idx, dist, pass);
   cudaError_t e = cudaGetLastError();

@@ -129,6 +129,7 @@ int launch_brute_track(const PyrView& from, const PyrView& to, int from_first, i
                        int n_per_pair, const float* from_xy, float* to_xy, const float* coarse,
                        int n_coarse, const float* fine, int n_fine, int32_t* status, float* best_sad,
                        unsigned long long* positions, cudaStream_t s);
+int hamming_set_impl(int impl);  // hamming.cu: 0 by size, 1 ALU kernel, 2 tensor-core kernel; returns the previous value
 int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int ratio_num,
                       int ratio_den, int max_dist, int32_t* idx, int32_t* dist, uint8_t* pass,
                       void** ws, size_t* ws_cap, cudaStream_t s);

@@ -440,8 +440,18 @@ def test_brute_track_reference_schedule_bit_exact(fe, po, sfe, synth):
     assert g["positions"] == o["positions"] and g["positions"] >= 6 * 1600 * 1600
 
 
-@pytest.mark.parametrize("nq,nt,batch", [(2000, 2000, 1), (777, 1301, 3), (1, 1, 1), (5, 0, 1), (300, 1, 2), (4096, 70000, 1)])
-def test_hamming_bit_exact(fe, po, synth, nq, nt, batch):
+@pytest.fixture(params=["alu", "mma"])
+def hamming_kernel(request, fe):
+    """Runs a test once per matcher kernel: the integer-ALU kernel (hamming.cu) and the tcgen05 int8 contraction
+    (hamming_mma.cu) must both be bit-identical to the oracle."""
+    prev = fe.hamming_impl({"alu": 1, "mma": 2}[request.param])
+    yield request.param
+    fe.hamming_impl(prev)
+
+
+@pytest.mark.parametrize("nq,nt,batch", [(2000, 2000, 1), (777, 1301, 3), (1, 1, 1), (5, 0, 1), (300, 1, 2), (4096, 70000, 1),
+                                         (128, 256, 1), (129, 257, 2), (500, 513, 40), (3000, 255, 1)])
+def test_hamming_bit_exact(fe, po, synth, hamming_kernel, nq, nt, batch):
     t = synth.make_descriptors(1, max(nt * batch, 1), dup_frac=0.05)[:nt * batch]
     q = synth.make_descriptors(2, nq * batch, dup_frac=0.3, source=t if nt else None)
     idx, dist, ok = fe.match_hamming256(q, t, 4, 5, 80, batch=batch)
@@ -472,7 +482,27 @@ def test_config3_1080p_8_levels_5000_features_bit_exact(fe, po, synth):
     assert g["accepted"].mean() > 0.8
 
 
-def test_config5_hamming_1m_x_1m_properties(fe, po, synth):
+def test_hamming_extreme_rows_bit_exact(fe, po, synth, hamming_kernel):
+    """All-zero / all-one rows, distances 0 and 256, every tie broken by the lowest train index: the corners of the
+    accumulator range of the int8 contraction (8192 d + j - 128 - 2^20, d = 0 ... 256, j = 0 ... 255)."""
+    rng = np.random.default_rng(3)
+    t = synth.make_descriptors(5, 1024, dup_frac=0.0)
+    t[0] = 0; t[1] = 0xffffffff; t[255] = 0; t[256] = 0xffffffff; t[511] = t[700]; t[1023] = 0
+    q = synth.make_descriptors(6, 640, dup_frac=0.0)
+    q[0] = 0; q[1] = 0xffffffff; q[2] = t[700]; q[3] = ~t[700]; q[639] = 0xffffffff
+    q[4:132] = t[rng.integers(0, 1024, 128)]
+    idx, dist, ok = fe.match_hamming256(q, t, 4, 5, 80)
+    oi, od, oo = po.hamming256_top2(q, t, 4, 5, 80)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od) and np.array_equal(ok, oo)
+    assert tuple(idx[0]) == (0, 255) and tuple(dist[0]) == (0, 0) and tuple(idx[2]) == (511, 700)
+    # one train tile whose every row ties at the maximum distance
+    t2 = np.zeros((300, 8), np.uint32)
+    q2 = np.full((130, 8), 0xffffffff, np.uint32)
+    i2, d2, _ = fe.match_hamming256(q2, t2, 4, 5, 80)
+    assert (i2 == np.array([0, 1])).all() and (d2 == 256).all()
+
+
+def test_config5_hamming_1m_x_1m_properties(fe, po, synth, hamming_kernel):
     """BASELINE config 5 at full size on one GPU (10^12 comparisons): the oracle cannot finish that, so the result is
     checked through size-independent properties -- planted duplicates are found at distance 0 at the LOWEST train index
     that holds them, distances are ordered, the ratio flag is consistent with the returned distances -- and 256 randomly
