@@ -37,6 +37,14 @@ static inline float tree32(float* p) {
   return p[0];
 }
 
+/* The Hessian tracker (P1) declares the other balanced tree: adjacent lanes first, strides 1,2,4,8,16 -- the order its
+ * CUDA kernel gets from transposing the lane partials through shared memory (track_hessian.cu reduce_stats). */
+static inline float tree32_adj(float* p) {
+  for (int off = 1; off < 32; off <<= 1)
+    for (int l = 0; l < 32; l += 2 * off) p[l] = p[l] + p[l + off];
+  return p[0];
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -349,7 +357,7 @@ const float* orc_pyr_plane(const orc_pyr* p, int level, int plane) {
 
 /* hessian.h:85-91: mean = sum/len, sumsq = sum(d*d)/len over ALL 169 entries (zeros included),
  * float accumulators, in the declared lane/tree order. */
-static void patch_stats(const float* d, float* mean, float* sumsq) {
+static void patch_stats_tree(const float* d, float* mean, float* sumsq, int adjacent) {
   float s[32], q[32];
   for (int l = 0; l < 32; ++l) s[l] = q[l] = 0.f;
   for (int i = 0; i < ORC_PLEN; ++i) {
@@ -357,9 +365,10 @@ static void patch_stats(const float* d, float* mean, float* sumsq) {
     s[l] = s[l] + d[i];
     q[l] = fmaf(d[i], d[i], q[l]);
   }
-  *mean = tree32(s) / (float)ORC_PLEN;
-  *sumsq = tree32(q) / (float)ORC_PLEN;
+  *mean = (adjacent ? tree32_adj(s) : tree32(s)) / (float)ORC_PLEN;
+  *sumsq = (adjacent ? tree32_adj(q) : tree32(q)) / (float)ORC_PLEN;
 }
+static void patch_stats(const float* d, float* mean, float* sumsq) { patch_stats_tree(d, mean, sumsq, 0); }  /* klt.h, brute.h */
 
 /* ------------------------------------------------------------------ P1 HessianTracker */
 
@@ -395,7 +404,7 @@ static void hes_get_patch(const orc_plane* g, float px, float py, float* data, f
   }
   if (rw > 0 && rh > 0)
     orc_rect_subpix(g->data, g->w, g->h, rw, rh, px, py, data + rx + ry * n, n); /* :77-83 */
-  patch_stats(data, mean, sumsq);
+  patch_stats_tree(data, mean, sumsq, 1);
 }
 
 void orc_hes_get_patch(const orc_pyr* p, int level, float x, float y, float* data169, float* mean,
@@ -417,7 +426,7 @@ float orc_hes_score(const float* p1, float mean1, float sumsq1, const float* p2,
     diff = diff * diff;
     s[i & 31] = fmaf(diff, mask[i], s[i & 31]);
   }
-  return tree32(s);
+  return tree32_adj(s);
 }
 
 /* hessian.h:147-172.  out6 = dx,dy,dxx,dxy,dyx,dyy (each rounded to float as the reference

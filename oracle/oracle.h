@@ -33,8 +33,10 @@
  *                       top-right corner quirk                          bit-exact
  * Reductions over the 169 patch pixels use a DECLARED order:
  * pixel i goes to lane i%32, each lane accumulates its pixels in increasing i,
- * then a pairwise tree with strides 16,8,4,2,1.  The reference itself is built
- * with -ffast-math, so it has no defined order of its own.
+ * then a balanced pairwise tree over the 32 lanes: strides 16,8,4,2,1 for klt.h and brute.h
+ * (tree32, what a __shfl_xor butterfly computes), strides 1,2,4,8,16 -- adjacent lanes first --
+ * for hessian.h (tree32_adj, what the live tracker's shared-memory transposition computes).
+ * The reference itself is built with -ffast-math, so it has no defined order of its own.
  */
 #ifndef SLAMFE_ORACLE_H_
 #define SLAMFE_ORACLE_H_

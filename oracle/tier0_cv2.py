@@ -43,14 +43,25 @@ def tree32(lanes):
     return f32(p[0])
 
 
-def lane_sum(vals, acc_fn):
-    """Declared reduction: pixel i -> lane i%32, sequential within a lane, then tree32."""
+def tree32_adj(lanes):
+    """The Hessian tracker's tree (oracle.h): adjacent lanes first, strides 1,2,4,8,16."""
+    p = np.array(lanes, dtype=np.float32)
+    off = 1
+    while off < 32:
+        p[::2 * off] = p[::2 * off] + p[off::2 * off]
+        off <<= 1
+    return f32(p[0])
+
+
+def lane_sum(vals, acc_fn, adjacent=False):
+    """Declared reduction: pixel i -> lane i%32, sequential within a lane, then tree32 (klt.h, brute.h) or
+    tree32_adj (hessian.h)."""
     vals = np.asarray(vals, np.float32)
     lanes = np.zeros(32, np.float32)
     for k in range(0, LEN, 32):
         chunk = vals[k:k + 32]
         lanes[:len(chunk)] = acc_fn(lanes[:len(chunk)], chunk, k)
-    return tree32(lanes)
+    return tree32_adj(lanes) if adjacent else tree32(lanes)
 
 
 def mask13():
@@ -124,10 +135,10 @@ def pyramid_brute(bgr, depth):
 
 # ------------------------------------------------------------------ patches
 
-def patch_stats(data):
+def patch_stats(data, adjacent=False):
     d = np.asarray(data, np.float32).ravel()
-    s = lane_sum(d, lambda acc, x, k: acc + x)
-    q = lane_sum(d, lambda acc, x, k: fma(x, x, acc))
+    s = lane_sum(d, lambda acc, x, k: acc + x, adjacent)
+    q = lane_sum(d, lambda acc, x, k: fma(x, x, acc), adjacent)
     return f32(s / f32(LEN)), f32(q / f32(LEN))
 
 
@@ -147,7 +158,7 @@ def hes_get_patch(img, x, y):
         ry, rh = d, N - d
     if rw > 0 and rh > 0:
         data[ry:ry + rh, rx:rx + rw] = cv2.getRectSubPix(img, (rw, rh), (float(px), float(py)))
-    m, q = patch_stats(data)
+    m, q = patch_stats(data, adjacent=True)
     return data, m, q
 
 
@@ -174,7 +185,7 @@ def hes_score(p1, m1, q1, p2, m2, q2):
         kk = keep[k:k + len(x)]
         return np.where(kk, fma(x, mask[k:k + len(x)], acc), acc)
 
-    return lane_sum(term, acc_fn)
+    return lane_sum(term, acc_fn, adjacent=True)
 
 
 def klt_sad(p1, p2):

@@ -32,7 +32,10 @@
 
 namespace {
 
-constexpr int TRK_WARPS = 4;
+#ifndef TRK_WARPS_D
+#define TRK_WARPS_D 4  // warps (= features in flight) per CTA
+#endif
+constexpr int TRK_WARPS = TRK_WARPS_D;
 #ifndef TRK_MINB
 #define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
 #endif
@@ -46,7 +49,13 @@ struct WarpScratch {
   float v[6 * SFE_SLOTS * 32];       // general route: patch value of shift s, slot k, lane l at [(s*6+k)*32 + l]
   float T[SFE_SLOTS * 32];           // template patch and its effective mask, slot k of lane l at [k*32 + l]
   float mkT[SFE_SLOTS * 32];
+  // transposing reductions: lane l parks partial sum j at [j * RS + l]; rows 6, 7, 14, 15 of the statistics block and
+  // rows 6, 7 of the score block are never written and stay zero (they feed the idle lanes of the read-back)
+  float red[16 * 36];
+  float red2[8 * 36];
 };
+constexpr int RS = 36;  // row stride of the reduction blocks: 16-byte aligned rows, and the float4 read-back of a quarter-warp
+                        // (4 rows x 2 halves, or 2 rows x 4 quarters) touches 32 distinct banks
 
 // Per-lane patch coordinates, packed: byte k of (lo, hi) is pr * 16 + pc of the lane's slot k (i = lane + 32 k,
 // pr = i / 13, pc = i % 13) -- with the tile's row stride of 16 that byte IS the tap offset inside the footprint.
@@ -236,15 +245,48 @@ __device__ __forceinline__ double div_h(double x) {
   return __fma_rn(r, y, q);
 }
 
-// Two warp sums in one packed reduction (same 16,8,4,2,1 tree per value as warp_sum):
-// returns the total of `a` in lanes < 16 and of `b` in lanes >= 16.
+// Declared reduction order of this tracker (oracle.h, tree32_adj): per-lane partial sums, then the balanced pairwise tree
+// that pairs ADJACENT lanes first -- ((l0+l1)+(l2+l3)) ... strides 1,2,4,8,16.  The reference is built with -ffast-math and
+// has no order of its own; this one is chosen because it maps onto a transposition through shared memory: every lane
+// parks its partial sums (one conflict-free STS each), then a few lanes per value read back 16 (or 8) consecutive lanes'
+// partials as float4 and add them as a tree in registers -- 12 STS + 4 LDS.128 + 16 FADD + 1 SHFL for the twelve patch
+// statistics, where the transposing shuffle butterfly needed 16 SHFL + 30 selects + 16 FADD (-9 % executed instructions).
+__device__ __forceinline__ float tree4(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+
+// 12 statistics (rows 0-5: sums, rows 8-13: sums of squares).  Returns the total of row (lane >> 1).
+__device__ __forceinline__ float reduce_stats(WarpScratch& S, const float (&st)[16], int lane) {
+  float* w = S.red + lane;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    w[j * RS] = st[j];
+    w[(8 + j) * RS] = st[8 + j];
+  }
+  __syncwarp();
+  const float4* r = reinterpret_cast<const float4*>(S.red + (lane >> 1) * RS + (lane & 1) * 16);
+  const float4 a = r[0], b = r[1], c = r[2], d = r[3];
+  const float h = (tree4(a) + tree4(b)) + (tree4(c) + tree4(d));  // 16 lanes
+  return h + __shfl_xor_sync(SFE_FULL, h, 1);
+}
+// 6 scores.  Returns the total of row (lane >> 2) (lanes 24-31: zero).
+__device__ __forceinline__ float reduce_scores(WarpScratch& S, const float (&part)[8], int lane) {
+  float* w = S.red2 + lane;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) w[j * RS] = part[j];
+  __syncwarp();
+  const float4* r = reinterpret_cast<const float4*>(S.red2 + (lane >> 2) * RS + (lane & 3) * 8);
+  const float4 a = r[0], b = r[1];
+  float q = tree4(a) + tree4(b);  // 8 lanes
+  q = q + __shfl_xor_sync(SFE_FULL, q, 1);
+  return q + __shfl_xor_sync(SFE_FULL, q, 2);
+}
+// Two warp sums in one packed butterfly, same tree: even lanes end with the total of `a`, odd lanes with that of `b`.
 __device__ __forceinline__ float packed_reduce2(float a, float b, int lane) {
-  const bool h16 = lane & 16;
-  float r = (h16 ? b : a) + __shfl_xor_sync(SFE_FULL, h16 ? a : b, 16);
-  r = r + __shfl_xor_sync(SFE_FULL, r, 8);
-  r = r + __shfl_xor_sync(SFE_FULL, r, 4);
+  const bool odd = lane & 1;
+  float r = (odd ? b : a) + __shfl_xor_sync(SFE_FULL, odd ? a : b, 1);
   r = r + __shfl_xor_sync(SFE_FULL, r, 2);
-  return r + __shfl_xor_sync(SFE_FULL, r, 1);
+  r = r + __shfl_xor_sync(SFE_FULL, r, 4);
+  r = r + __shfl_xor_sync(SFE_FULL, r, 8);
+  return r + __shfl_xor_sync(SFE_FULL, r, 16);
 }
 
 // Finite differences of the six scores (hessian.h:163-169), lane-parallel.  Stage A: lane j < 8
@@ -341,7 +383,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     }
     const float red = div169(packed_reduce2(sm, sq, lane));
     t.mean = __shfl_sync(SFE_FULL, red, 0);
-    t.sumsq = __shfl_sync(SFE_FULL, red, 16);
+    t.sumsq = __shfl_sync(SFE_FULL, red, 1);
     return 0.f;
   }
 
@@ -397,8 +439,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     st[8 + 2 * p] = sq.x;
     st[8 + 2 * p + 1] = sq.y;
   }
-  st[6] = st[7] = st[14] = st[15] = 0.f;
-  const float red = packed_reduce16(st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
+  const float red = reduce_stats(S, st, lane);  // lanes 2s,2s+1: sum_s; lanes 16+2s,17+2s: sumsq_s
   const float other = __shfl_xor_sync(SFE_FULL, red, 16);
   // lane-parallel alpha/beta (hessian.h:131-132): lanes 2s (s < 6) hold the values of shift s; lanes >= 12
   // hold padding and get benign operands so the IEEE divide/sqrt stay on their fast paths
@@ -450,13 +491,15 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
       for (int j = 0; j < 6; ++j) part[j] = s == j ? p : part[j];
     }
   }
-  const float sc = packed_reduce8(part, lane);  // score s in lanes 4s..4s+3
+  const float sc = reduce_scores(S, part, lane);  // score s in lanes 4s..4s+3
   finite_differences(sc, lane, d);
   return __shfl_sync(SFE_FULL, sc, 0);
 }
 
 __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
   if (lane < TS + 2) S.zero[lane] = 0.f;
+  for (int i = lane; i < 16 * RS; i += 32) S.red[i] = 0.f;
+  for (int i = lane; i < 8 * RS; i += 32) S.red2[i] = 0.f;
   __syncwarp();
 }
 
