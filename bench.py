@@ -77,6 +77,15 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peaks():
+    """int8 tensor peak for the matcher's roofline: twice the measured dense bf16 rate (Tops/s)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return 2.0 * float(json.load(f)["bf16_tflops"]), "2 x measured bf16 (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a
     thread every 2 ms (the timed region is ~100 ms; nvidia-smi -lms cannot sample that fast), nvidia-smi as a
@@ -349,6 +358,7 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_src = peaks()
+        tensor_peak, tensor_src = tensor_peaks()
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
         pyr_bytes = 2 * B * (3 * W * H + 4 * sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(DEPTH)))
@@ -360,7 +370,10 @@ def run_gpu(args):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
         issue_peak = sms * 4 * mhz * 1e6
-        usable = cal is not None and not cal["stale"] and int(cal.get("batch_pairs", -1)) == B
+        # a calibration of another tracker build or batch size is still reported (the instruction count per Newton step
+        # moves by a few percent between builds) but flagged: "stale": true means "re-run tools/ncu_calibrate.py"
+        usable = cal is not None and "track_fb_kernel" in cal
+        stale = usable and (bool(cal["stale"]) or int(cal.get("batch_pairs", -1)) != B)
         per_step = float(cal["track_fb_kernel"]["warp_instructions_per_newton_step"]) if usable else None
         issue_achieved = per_step * newton / (trk_ms * 1e-3) if usable else None
         e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
@@ -393,8 +406,9 @@ def run_gpu(args):
                          "unit": "warp-instructions/s", "frac": issue_achieved / issue_peak if usable else None,
                          "traffic": float(cal["track_fb_kernel"]["dram_bytes"]) if usable else None,
                          "warp_instructions_per_newton_step": per_step,
-                         "calibration": None if cal is None else {"file": "profiles/traffic.json", "stale": bool(cal["stale"]),
-                                                                  "batch_pairs": cal.get("batch_pairs")},
+                         "calibration": None if cal is None else {"file": "profiles/traffic.json", "stale": bool(stale),
+                                                                  "batch_pairs": cal.get("batch_pairs"),
+                                                                  "tracker_source_hash": cal.get("tracker_source_hash")},
                          "share_of_step": trk_ms / ms_step,
                          "newton_steps_per_sec": newton / (trk_ms * 1e-3),
                          "bilinear_samples_per_sec": (newton * 6 * 169) / (trk_ms * 1e-3),
@@ -408,6 +422,18 @@ def run_gpu(args):
                                  "traffic": float(cal["pyramid_build"]["dram_bytes"]) if usable and "pyramid_build" in cal else None,
                                  "algorithmic_bytes": pyr_bytes, "peak_source": peak_src,
                                  "share_of_step": pyr_ms / ms_step},
+            # the descriptor matcher: an exact int8 contraction on the tensor cores (tcgen05.mma kind::i8, K = 288 per
+            # comparison incl. the index block).  achieved = 2 x 288 integer operations per comparison / its CUDA-event
+            # time; peak = twice the measured dense bf16 rate (int8 runs at twice the bf16 rate on sm_100).  The ncu capture
+            # says what actually bounds it: the ALU pipe of the unpack + top-2 epilogue warps, not the tensor pipe.
+            "roofline_hamming": {"kernel": "hamming_mma_kernel (+ hamming_finalize_kernel)", "bound": "tensor",
+                                 "achieved": B * NFEAT * NFEAT * 576.0 / (ham_ms * 1e-3) / 1e12, "peak": tensor_peak,
+                                 "unit": "Tops/s (int8)", "frac": B * NFEAT * NFEAT * 576.0 / (ham_ms * 1e-3) / 1e12 / tensor_peak,
+                                 "peak_source": tensor_src, "comparisons_per_sec": B * NFEAT * NFEAT / (ham_ms * 1e-3),
+                                 "traffic": float(cal["hamming_mma_kernel"]["dram_bytes_read"] + cal["hamming_mma_kernel"]["dram_bytes_write"])
+                                 if usable and "hamming_mma_kernel" in cal else None,
+                                 "limiter": "ALU pipe of the worker warps (profiles/ham_r2*_summary.txt)",
+                                 "share_of_step": ham_ms / ms_step},
             "other_configs": other,
         }
         if not args.no_cpu and world == 1:
