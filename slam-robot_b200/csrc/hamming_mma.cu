@@ -2,25 +2,27 @@
 // cores (tcgen05.mma kind::i8, accumulators in tensor memory), with the top-2 scan as its epilogue.
 //
 // The Hamming distance of two bit rows is bilinear once the bits are written as signs: with q' = 1 - 2*qbit and
-// t' = 1 - 2*tbit,  sum_k q'_k t'_k = 256 - 2 d.  The query tile is unpacked to a_k = -64 q'_k, the train tile to
-// b_k = +64 t'_k (signed bytes), so  sum_k a_k b_k = 8192 d - 2^20  -- every partial sum is an integer below 2^21,
+// t' = 1 - 2*tbit,  sum_k q'_k t'_k = 256 - 2 d.  The query tile is unpacked to a_k = -8 q'_k, the train tile to
+// b_k = +8 t'_k (signed bytes), so  sum_k a_k b_k = 128 d - 2^14  -- every partial sum is an integer of at most 15 bits,
 // s32 accumulation is exact, there is no rounding anywhere.  One more K block carries the tie rule: a = (1, 0, ...),
-// b = (j - 128, 0, ...) with j the train row's index inside its 256-row tile, so the accumulator the tensor core
+// b = (j mod 128, 0, ...) with j the train row's index inside its 256-row tile, so the accumulator the tensor core
 // hands back is
-//        acc[i][j] = 8192 d(i,j) + j - 128 - 2^20
-// which orders the tile's columns by (distance, train index) -- exactly the packed key of hamming.cu
-// (lowest train index wins ties, cv2.BFMatcher's rule; oracle.c orc_hamming256_top2).  The epilogue therefore is
-// nothing but a running two-smallest over raw accumulators (5 integer min/max per TWO columns, no decode, no index
-// arithmetic); the two winners of a tile are decoded once per tile into the global keys dist << 22 | index.
+//        acc[i][j] = 128 d(i,j) + (j mod 128) - 16384        in [-16384, 16511]: a signed 16-bit number
+// which orders the 128 columns a thread scans by (distance, train index) -- exactly the packed key of hamming.cu
+// (lowest train index wins ties, cv2.BFMatcher's rule; oracle.c orc_hamming256_top2).  Because the key fits 16 bits,
+// tcgen05.ld.pack::16b delivers TWO columns per register and the scan is a running two-smallest in both halves of a
+// register at once (VIMNMX.S16x2 / VIMNMX3.S16x2: 5 instructions per FOUR columns, no decode, no index arithmetic); the
+// winners of a tile are decoded once per tile into the global keys dist << 22 | index.
 //
-// Roles (288 threads, one CTA per SM, persistent over (batch, 128-query tile, train split) items):
-//   warps 0-7  unpack the next 256-row train tile (bits -> signed bytes, shared memory in the no-swizzle K-major
+// Roles (544 threads, one CTA per SM, persistent over (batch, 128-query tile, train split) items):
+//   warps 0-15 unpack the next 256-row train tile (bits -> signed bytes, shared memory in the no-swizzle K-major
 //              core-matrix layout the MMA descriptors name), then scan the previous tile's accumulators: warp w reads
-//              TMEM lanes 32 (w % 4).. with tcgen05.ld -- one query row per thread -- columns 128 (w / 4)..
-//   warp 8     waits for a full stage, issues 9 x tcgen05.mma (M 128, N 256, K 32) into one half of the 512 TMEM
+//              TMEM lanes 32 (w % 4).. with tcgen05.ld -- one query row per thread -- columns 64 (w / 4)..
+//   warp 16    waits for a full stage, issues 9 x tcgen05.mma (M 128, N 256, K 32) into one half of the 512 TMEM
 //              columns and commits them to the stage's mbarrier.
 // The train stages, the accumulators and the query tile are double-buffered, so the tensor core works on tile g
-// while the workers scan tile g-1 and unpack tile g+1, across item boundaries as well.
+// while the workers scan tile g-1 and unpack tile g+1, across item boundaries as well.  What bounds it is the ALU pipe
+// of the worker warps (profiles/ham_r2*): the nine UTCIMMA per tile hide completely behind unpack + scan.
 #include "sfe_common.cuh"
 
 namespace {
@@ -28,14 +30,21 @@ namespace {
 constexpr int MM_M = 128;            // queries per item (TMEM lanes)
 constexpr int MM_N = 256;            // train rows per tile (TMEM columns of one accumulator)
 constexpr int MM_KB = 9;             // K blocks of 32 bytes: 8 x 32 descriptor bits + the index block
-constexpr int MM_WORKERS = 256;      // threads of warps 0-7
+#ifndef MM_PARTS_D
+#define MM_PARTS_D 4
+#endif
+constexpr int MM_PARTS = MM_PARTS_D;             // worker warps per TMEM lane quadrant: each scans MM_N / MM_PARTS columns
+constexpr int MM_WWARPS = 4 * MM_PARTS;          // worker warps (warp MM_WWARPS issues the MMAs)
+constexpr int MM_WORKERS = 32 * MM_WWARPS;
 constexpr int MM_THREADS = MM_WORKERS + 32;
+constexpr int MM_PCOLS = MM_N / MM_PARTS;        // columns per part: 64 (one packed TMEM load) or 128 (two)
+static_assert(MM_PARTS == 2 || MM_PARTS == 4, "2 or 4 column parts");
 constexpr int MM_A_BYTES = MM_M * 32 * MM_KB;   // 36,864
 constexpr int MM_B_BYTES = MM_N * 32 * MM_KB;   // 73,728
 constexpr int MM_SMEM = 2 * MM_A_BYTES + 2 * MM_B_BYTES + 128;   // + barriers and the TMEM address
 constexpr int MM_IDX_BITS = 22;
 constexpr uint32_t MM_KEY_NONE = 0xffffffffu;
-constexpr int MM_BIAS = (1 << 20) + 128;        // acc + MM_BIAS = 8192 d + j
+constexpr int MM_BIAS = 16384;                  // acc + MM_BIAS = 128 d + (j mod 128)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,9 +84,10 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+// 64 accumulator columns as 32 registers: register r = low 16 bits of column 2r | low 16 bits of column 2r + 1 << 16
+__device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
       "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
@@ -88,26 +98,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- bits -> signed bytes -------------------------------------------------------------------------------------------
-// Four bits to four bytes: n * 0x10204080 puts bit b of the 4-bit value n at bit 8b + 7 -- the four shifted copies of a
-// 4-bit value do not overlap, so nothing carries (a wider operand would: bit 0 << 14 meets bit 7 << 7); masked, that is
-// 0x80 per set bit; the xor maps {0, 0x80} to {-64, +64} or the reverse.
-template <uint32_t XORC>
+// Four bits to four bytes: n * 0x00204081 puts bit b of the 4-bit value n at bit 8b -- the four shifted copies of a 4-bit
+// value do not overlap, so nothing carries (a wider operand would: bit 0 << 14 meets bit 7 << 7); masked, that is one
+// byte of 0 / 1 per bit; a multiply-add maps {0, 1} to {+8, -8} (train rows, b = +8 t') or {-8, +8} (query rows,
+// a = -8 q') without a borrow between the bytes.  Two of the five operations are integer multiply-adds, which issue on
+// the FMA pipe -- the ALU pipe is what bounds this kernel.
+template <bool QUERY>
 __device__ __forceinline__ uint32_t spread4(uint32_t nibble) {
-  return ((nibble * 0x10204080u) & 0x80808080u) ^ XORC;
+  const uint32_t y = (nibble * 0x00204081u) & 0x01010101u;
+  return QUERY ? 0xF8F8F8F8u - y * 0xF0u : y * 0xF0u + 0x08080808u;
 }
 // One 32-bit descriptor word = one K block of one row: 32 signed bytes, stored as the row's two 16-byte chunks.
-template <uint32_t XORC>
+template <bool QUERY>
 __device__ __forceinline__ void unpack_word(uint32_t w, uint8_t* blk_row /* block base + row-group + row-in-group */) {
   uint4 c0, c1;
-  c0.x = spread4<XORC>(w & 0xfu);         c0.y = spread4<XORC>((w >> 4) & 0xfu);
-  c0.z = spread4<XORC>((w >> 8) & 0xfu);  c0.w = spread4<XORC>((w >> 12) & 0xfu);
-  c1.x = spread4<XORC>((w >> 16) & 0xfu); c1.y = spread4<XORC>((w >> 20) & 0xfu);
-  c1.z = spread4<XORC>((w >> 24) & 0xfu); c1.w = spread4<XORC>(w >> 28);
+  c0.x = spread4<QUERY>(w & 0xfu);         c0.y = spread4<QUERY>((w >> 4) & 0xfu);
+  c0.z = spread4<QUERY>((w >> 8) & 0xfu);  c0.w = spread4<QUERY>((w >> 12) & 0xfu);
+  c1.x = spread4<QUERY>((w >> 16) & 0xfu); c1.y = spread4<QUERY>((w >> 20) & 0xfu);
+  c1.z = spread4<QUERY>((w >> 24) & 0xfu); c1.w = spread4<QUERY>(w >> 28);
   *reinterpret_cast<uint4*>(blk_row) = c0;
   *reinterpret_cast<uint4*>(blk_row + 128) = c1;
 }
-constexpr uint32_t XOR_A = 0xC0C0C0C0u;  // query: bit 0 -> -64, bit 1 -> +64   (a = -64 q')
-constexpr uint32_t XOR_B = 0x40404040u;  // train: bit 0 -> +64, bit 1 -> -64   (b = +64 t')
+constexpr bool XOR_A = true;   // query rows
+constexpr bool XOR_B = false;  // train rows
 
 // Operand tile layout (R rows): block kb at kb * R * 32; inside a block row r sits at (r / 8) * 256 + (r % 8) * 16, its
 // second K chunk 128 bytes further: LBO = 128, SBO = 256.
@@ -133,17 +146,18 @@ __device__ __forceinline__ void top2_u(uint32_t key, uint32_t& k1, uint32_t& k2)
   k2 = min(k2, hi);
 }
 
-// Two smallest of a stream, two columns per step: 5 integer min/max (one of them three-input).
-__device__ __forceinline__ void top2_pair(int a, int b, int& k1, int& k2) {
-  const int lo = min(a, b), hi = max(a, b);
-  const int t = max(k1, lo);
-  k2 = min(min(k2, hi), t);
-  k1 = min(k1, lo);
+// Two smallest of a stream in both 16-bit halves of a register at once, two registers (four columns) per step:
+// 4 x VIMNMX.S16x2 + 1 x VIMNMX3.S16x2.
+__device__ __forceinline__ void top2_pair_s16x2(uint32_t a, uint32_t b, uint32_t& k1, uint32_t& k2) {
+  const uint32_t lo = __vmins2(a, b), hi = __vmaxs2(a, b);
+  const uint32_t t = __vmaxs2(k1, lo);
+  k2 = __vimin3_s16x2(k2, hi, t);
+  k1 = __vmins2(k1, lo);
 }
 
 __global__ void __launch_bounds__(MM_THREADS, 1)
 hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt, int batch, int splits,
-                   int per /* train rows per split, a multiple of MM_N */, uint2* __restrict__ keys /* [batch][2*splits][nq] */) {
+                   int per /* train rows per split, a multiple of MM_N */, uint2* __restrict__ keys /* [batch][MM_PARTS*splits][nq] */) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;                       // 2 query tiles
   uint8_t* sB = smem + 2 * MM_A_BYTES;      // 2 train stages
@@ -160,11 +174,11 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     mbar_init(bar_done + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == MM_WWARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // K block 8: a = (1, 0, ..., 0) for every query row, b = (j - 128, 0, ..., 0) for train row j of a tile
+  // K block 8: a = (1, 0, ..., 0) for every query row, b = (j mod 128, 0, ..., 0) for train row j of a tile
   for (int r = tid; r < 2 * MM_M; r += MM_THREADS) {
     uint8_t* p = sA + (r / MM_M) * MM_A_BYTES + 8 * MM_M * 32 + row_off(r % MM_M);
     *reinterpret_cast<uint4*>(p) = make_uint4(1u, 0u, 0u, 0u);
@@ -173,7 +187,7 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
   for (int r = tid; r < 2 * MM_N; r += MM_THREADS) {
     const int j = r % MM_N;
     uint8_t* p = sB + (r / MM_N) * MM_B_BYTES + 8 * MM_N * 32 + row_off(j);
-    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)((j - 128) & 0xff), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)(j & 127), 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_async_smem();
@@ -185,7 +199,7 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
   const int mtiles = (nq + MM_M - 1) / MM_M;
   const int nitems = batch * mtiles * splits;
 
-  if (warp == 8) {
+  if (warp == MM_WWARPS) {
     // ===== MMA issuer =====
     uint32_t g = 0;
     int seq = 0;
@@ -209,9 +223,8 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     }
   } else {
     // ===== workers: unpack tile g, scan tile g-1 =====
-    const uint4* q4 = reinterpret_cast<const uint4*>(q);
     const uint4* t4 = reinterpret_cast<const uint4*>(t);
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;                       // the query row (TMEM lane) this thread scans
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t g = 0;
@@ -226,33 +239,42 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
       mbar_wait(bar_done + 8 * s, ((g - 1) >> 1) & 1);
       tc_fence_after();
       if (p_first) K1 = K2 = MM_KEY_NONE;
-      int k1 = INT_MAX, k2 = INT_MAX;
-      const uint32_t tcol = tmem_base + lane_addr + s * MM_N + half * 128;
+      // this warp's MM_PCOLS columns, 64 per packed load; 0x7fff = no candidate in that half-register
+      uint32_t k1 = 0x7fff7fffu, k2 = 0x7fff7fffu;
+      const int col_base = part * MM_PCOLS;
+      const uint32_t tcol = tmem_base + lane_addr + s * MM_N + col_base;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = half * 128 + c * 32;
+      for (int c = 0; c < MM_PCOLS / 64; ++c) {
+        const int col0 = col_base + c * 64;
         if (col0 >= p_valid) break;  // warp-uniform
-        int v[32];
-        tmem_ld32(tcol + c * 32, v);
+        uint32_t v[32];
+        tmem_ld64_packed(tcol + c * 64, v);
         tmem_ld_wait();
-        if (col0 + 32 > p_valid) {
+        if (col0 + 64 > p_valid) {  // the last tile of a train range: columns >= p_valid hold stale rows
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = col0 + j < p_valid ? v[j] : INT_MAX;
+          for (int r = 0; r < 32; ++r) {
+            const int cc = col0 + 2 * r;
+            v[r] = cc + 1 < p_valid ? v[r] : (cc < p_valid ? (v[r] | 0x7fff0000u) & 0x7fffffffu : 0x7fff7fffu);
+          }
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) top2_pair(v[j], v[j + 1], k1, k2);
+        for (int r = 0; r < 32; r += 2) top2_pair_s16x2(v[r], v[r + 1], k1, k2);
       }
-      // the tile's two winners -> global keys (distance << 22 | train index)
-      if (k1 != INT_MAX) {
-        const uint32_t u = (uint32_t)(k1 + MM_BIAS);
-        top2_u(((u >> 13) << MM_IDX_BITS) | (uint32_t)(p_tbase + (int)(u & 8191u)), K1, K2);
-      }
-      if (k2 != INT_MAX) {
-        const uint32_t u = (uint32_t)(k2 + MM_BIAS);
-        top2_u(((u >> 13) << MM_IDX_BITS) | (uint32_t)(p_tbase + (int)(u & 8191u)), K1, K2);
+      // even and odd columns each kept their own two smallest: the tile's two winners are the two smallest of those four
+      {
+        const int a1 = (int)(short)(k1 & 0xffffu), b1 = (int)k1 >> 16, a2 = (int)(short)(k2 & 0xffffu), b2 = (int)k2 >> 16;
+        const int m1 = min(a1, b1), m2 = min(max(a1, b1), min(a2, b2));
+        if (m1 != 0x7fff) {
+          const uint32_t u = (uint32_t)(m1 + MM_BIAS);
+          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (col_base & 128) + (int)(u & 127u)), K1, K2);
+        }
+        if (m2 != 0x7fff) {
+          const uint32_t u = (uint32_t)(m2 + MM_BIAS);
+          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (col_base & 128) + (int)(u & 127u)), K1, K2);
+        }
       }
       if (p_last && p_q0 + row < nq)
-        keys[((size_t)p_b * (2 * splits) + 2 * p_split + half) * nq + p_q0 + row] = make_uint2(K1, K2);
+        keys[((size_t)p_b * (MM_PARTS * splits) + MM_PARTS * p_split + part) * nq + p_q0 + row] = make_uint2(K1, K2);
       tc_fence_before();  // the accumulator reads are ordered before the arrive that lets the next MMA overwrite them
     };
 
@@ -261,28 +283,28 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
       for (int t0 = I.t0; t0 < I.t1; t0 += MM_N, ++g) {
         const uint32_t s = g & 1;
         if (t0 == I.t0) {
-          // query tile of this item: thread -> (row tid % 128, words 4 (tid / 128) ..)
+          // query tile of this item: 128 rows x 8 words over the worker threads
+          constexpr int WPT = 8 * MM_M / MM_WORKERS;  // words per thread: 4 (256 workers) or 2 (512)
           const int r = tid & (MM_M - 1), hw = tid >> 7;
-          const uint4 w = __ldg(q4 + ((size_t)I.b * nq + min(I.q0 + r, nq - 1)) * 2 + hw);
+          const uint32_t* src = q + ((size_t)I.b * nq + min(I.q0 + r, nq - 1)) * 8 + WPT * hw;
           uint8_t* base = sA + (seq & 1) * MM_A_BYTES + row_off(r);
-          unpack_word<XOR_A>(w.x, base + (4 * hw + 0) * MM_M * 32);
-          unpack_word<XOR_A>(w.y, base + (4 * hw + 1) * MM_M * 32);
-          unpack_word<XOR_A>(w.z, base + (4 * hw + 2) * MM_M * 32);
-          unpack_word<XOR_A>(w.w, base + (4 * hw + 3) * MM_M * 32);
+          uint32_t w[WPT];
+          if (WPT == 4) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(src)); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
+          else { const uint2 x = __ldg(reinterpret_cast<const uint2*>(src)); w[0] = x.x; w[1] = x.y; }
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) unpack_word<XOR_A>(w[i], base + (WPT * hw + i) * MM_M * 32);
         }
         {
-          // train tile: thread -> row tid, all 8 words
-          const size_t tr = (size_t)I.b * nt + min(t0 + tid, nt - 1);
-          const uint4 w0 = __ldg(t4 + tr * 2), w1 = __ldg(t4 + tr * 2 + 1);
-          uint8_t* base = sB + s * MM_B_BYTES + row_off(tid);
-          unpack_word<XOR_B>(w0.x, base + 0 * MM_N * 32);
-          unpack_word<XOR_B>(w0.y, base + 1 * MM_N * 32);
-          unpack_word<XOR_B>(w0.z, base + 2 * MM_N * 32);
-          unpack_word<XOR_B>(w0.w, base + 3 * MM_N * 32);
-          unpack_word<XOR_B>(w1.x, base + 4 * MM_N * 32);
-          unpack_word<XOR_B>(w1.y, base + 5 * MM_N * 32);
-          unpack_word<XOR_B>(w1.z, base + 6 * MM_N * 32);
-          unpack_word<XOR_B>(w1.w, base + 7 * MM_N * 32);
+          // train tile: 256 rows x 8 words over the worker threads
+          constexpr int WPT = 8 * MM_N / MM_WORKERS;  // 8 or 4
+          const int r = tid & (MM_N - 1), hw = tid >> 8;
+          const uint4* src = t4 + ((size_t)I.b * nt + min(t0 + r, nt - 1)) * 2 + (WPT == 4 ? hw : 0);
+          uint8_t* base = sB + s * MM_B_BYTES + row_off(r);
+          uint32_t w[8];
+          { const uint4 x = __ldg(src); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
+          if (WPT == 8) { const uint4 x = __ldg(src + 1); w[4] = x.x; w[5] = x.y; w[6] = x.z; w[7] = x.w; }
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) unpack_word<XOR_B>(w[i], base + ((WPT == 4 ? 4 * hw : 0) + i) * MM_N * 32);
         }
         fence_async_smem();              // generic-proxy stores -> visible to the tensor core's async proxy
         mbar_arrive(bar_full + 8 * s);
@@ -300,7 +322,7 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MM_WWARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -308,9 +330,9 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
 
 }  // namespace
 
-// Launches the tensor-core matcher; writes [batch][2 * splits][nq] keys for hamming_finalize_kernel (hamming.cu), which
-// merges them exactly as it merges the ALU kernel's train splits.  Returns the number of key rows per query (2 * splits)
-// or a negative cudaError.
+// Launches the tensor-core matcher; writes [batch][MM_PARTS * splits][nq] keys for hamming_finalize_kernel (hamming.cu),
+// which merges them exactly as it merges the ALU kernel's train splits.  Returns the number of key rows per query
+// (MM_PARTS * splits) or a negative cudaError.
 int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int num_sms, void** ws, size_t* ws_cap,
                        cudaStream_t s) {
   static bool configured = false;
@@ -326,7 +348,7 @@ int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int
   if (batch * mtiles < num_sms) splits = min(ntiles, (num_sms + batch * mtiles - 1) / (batch * mtiles));
   const int per = ((ntiles + splits - 1) / splits) * MM_N;
   splits = (nt + per - 1) / per;
-  const size_t need = (size_t)batch * 2 * splits * nq * sizeof(uint2);
+  const size_t need = (size_t)batch * MM_PARTS * splits * nq * sizeof(uint2);
   if (need > *ws_cap) {
     if (*ws) cudaFree(*ws);
     cudaError_t e = cudaMalloc(ws, need);
@@ -336,5 +358,5 @@ int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int
   const int nitems = batch * mtiles * splits;
   hamming_mma_kernel<<<min(nitems, num_sms), MM_THREADS, MM_SMEM, s>>>(q, nq, t, nt, batch, splits, per, (uint2*)*ws);
   cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 2 * splits : -(int)e;
+  return e == cudaSuccess ? MM_PARTS * splits : -(int)e;
 }
