@@ -233,6 +233,27 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     int p_valid = 0, p_tbase = 0, p_b = 0, p_q0 = 0, p_split = 0;
     bool p_first = false, p_last = false, have_prev = false;
     uint32_t K1 = MM_KEY_NONE, K2 = MM_KEY_NONE;
+    uint4 nw0 = make_uint4(0u, 0u, 0u, 0u), nw1 = nw0;  // this thread's words of the next train tile
+    bool have_next = false;
+    auto load_train = [&](int b, int t0) {
+      constexpr int WPT = 8 * MM_N / MM_WORKERS;
+      const int r = tid & (MM_N - 1), hw = tid >> 8;
+      const uint4* src = t4 + ((size_t)b * nt + min(t0 + r, nt - 1)) * 2 + (WPT == 4 ? hw : 0);
+      nw0 = __ldg(src);
+      if (WPT == 8) nw1 = __ldg(src + 1);
+      have_next = true;
+    };
+
+    uint4 qw = make_uint4(0u, 0u, 0u, 0u);  // this thread's words of the next query tile
+    bool have_q = false;
+    auto load_query = [&](int b, int q0) {
+      constexpr int WPT = 8 * MM_M / MM_WORKERS;
+      const int r = tid & (MM_M - 1), hw = tid >> 7;
+      const uint32_t* src = q + ((size_t)b * nq + min(q0 + r, nq - 1)) * 8 + WPT * hw;
+      if (WPT == 4) qw = __ldg(reinterpret_cast<const uint4*>(src));
+      else { const uint2 x = __ldg(reinterpret_cast<const uint2*>(src)); qw.x = x.x; qw.y = x.y; }
+      have_q = true;
+    };
 
     auto scan_prev = [&]() {
       const uint32_t s = (g - 1) & 1;
@@ -283,31 +304,39 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
       for (int t0 = I.t0; t0 < I.t1; t0 += MM_N, ++g) {
         const uint32_t s = g & 1;
         if (t0 == I.t0) {
-          // query tile of this item: 128 rows x 8 words over the worker threads
+          // query tile of this item: 128 rows x 8 words over the worker threads (requested with the previous item's
+          // last train tile, except for this CTA's first item)
           constexpr int WPT = 8 * MM_M / MM_WORKERS;  // words per thread: 4 (256 workers) or 2 (512)
           const int r = tid & (MM_M - 1), hw = tid >> 7;
-          const uint32_t* src = q + ((size_t)I.b * nq + min(I.q0 + r, nq - 1)) * 8 + WPT * hw;
+          if (!have_q) load_query(I.b, I.q0);
+          have_q = false;
           uint8_t* base = sA + (seq & 1) * MM_A_BYTES + row_off(r);
-          uint32_t w[WPT];
-          if (WPT == 4) { const uint4 x = __ldg(reinterpret_cast<const uint4*>(src)); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
-          else { const uint2 x = __ldg(reinterpret_cast<const uint2*>(src)); w[0] = x.x; w[1] = x.y; }
+          const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
           for (int i = 0; i < WPT; ++i) unpack_word<XOR_A>(w[i], base + (WPT * hw + i) * MM_M * 32);
         }
         {
-          // train tile: 256 rows x 8 words over the worker threads
+          // train tile: 256 rows x 8 words over the worker threads; the words were requested one tile ago (the L2 round
+          // trip of these loads was the kernel's top stall when they were issued here)
           constexpr int WPT = 8 * MM_N / MM_WORKERS;  // 8 or 4
           const int r = tid & (MM_N - 1), hw = tid >> 8;
-          const uint4* src = t4 + ((size_t)I.b * nt + min(t0 + r, nt - 1)) * 2 + (WPT == 4 ? hw : 0);
+          if (!have_next) load_train(I.b, t0);
           uint8_t* base = sB + s * MM_B_BYTES + row_off(r);
-          uint32_t w[8];
-          { const uint4 x = __ldg(src); w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; }
-          if (WPT == 8) { const uint4 x = __ldg(src + 1); w[4] = x.x; w[5] = x.y; w[6] = x.z; w[7] = x.w; }
+          uint32_t w[8] = {nw0.x, nw0.y, nw0.z, nw0.w, nw1.x, nw1.y, nw1.z, nw1.w};
 #pragma unroll
           for (int i = 0; i < WPT; ++i) unpack_word<XOR_B>(w[i], base + ((WPT == 4 ? 4 * hw : 0) + i) * MM_N * 32);
         }
         fence_async_smem();              // generic-proxy stores -> visible to the tensor core's async proxy
         mbar_arrive(bar_full + 8 * s);
+        // request the next tile's rows (of this item, or the first tile of this CTA's next item) before the scan
+        have_next = false;
+        if (t0 + MM_N < I.t1) {
+          load_train(I.b, t0 + MM_N);
+        } else if (it + (int)gridDim.x < nitems) {
+          const Item N = item_of(it + gridDim.x, mtiles, splits, nt, per);
+          load_train(N.b, N.t0);
+          load_query(N.b, N.q0);
+        }
         if (have_prev) scan_prev();
         p_valid = min(MM_N, I.t1 - t0);
         p_tbase = t0;
