@@ -466,6 +466,22 @@ def other_configs(args, torch, dist, sfe, synth, fe, dev, rank, world, seq, h_pt
         "shard_pairs_per_rank": hi - lo, "timed": "%d calls of sfe_replay_sequence x %d pairs per rank (%.1f %% of the shard), "
         "max over ranks; no data-path collective" % (calls, B, 100.0 * calls * B / max(hi - lo, 1)),
         "projected_seconds_for_65536_pairs": total_pairs / rate}
+    # the same replay from the camera's native packed YUYV (video.cpp:187-223 on the device): 2 instead of 3 bytes per
+    # pixel cross the host link, which is what limits eight ranks of one box
+    yuyv = torch.empty((seq.shape[0], H, W, 2), dtype=torch.uint8).pin_memory()
+    yuyv[..., 0] = seq[..., 1]
+    yuyv[..., 1] = 128
+    fe.replay_sequence(yuyv, SEQ_STRIDE, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        fe.replay_sequence(yuyv, SEQ_STRIDE, h_pts, h_pts, DEPTH, LEVELS, THR, MAXIT, FB_MAX, n_per_pair=NFEAT, out=h_trk)
+    torch.cuda.synchronize()
+    (c4y_s,) = max_over_ranks([time.perf_counter() - t0])
+    out["C4_replay_yuyv"] = {"pairs_per_sec": world * B * calls / c4y_s, "unit": "frame pairs/s",
+                             "h2d_bytes_per_pair": int(yuyv[0].numel() * yuyv.shape[0] / B),
+                             "entry": "sfe_replay_sequence_yuyv (YUYV -> BGR on the device, then the same pipeline)"}
+    del yuyv
 
     # ---- C5: 1M x 1M descriptors, strong scaling: query rows sharded, train broadcast + rows all-gathered by NCCL
     # inside libslamfe (sfe_match_hamming256_sharded_dev); all collectives and kernels on one stream, CUDA-event timed
