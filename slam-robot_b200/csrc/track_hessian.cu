@@ -53,6 +53,10 @@ struct WarpScratch {
   // rows 6, 7 of the score block are never written and stay zero (they feed the idle lanes of the read-back)
   float red[16 * 36];
   float red2[8 * 36];
+  // lane-parallel results that every lane needs, handed over with one store and a few broadcast loads instead of one
+  // shuffle per value: geo[j] = {a, 1-a, i0, r} of axis variant j (0..2: x, 4..6: y), ab = -alpha (0..5), -beta (8..13)
+  float4 geo[8];
+  float ab[16];
 };
 constexpr int RS = 36;  // row stride of the reduction blocks: 16-byte aligned rows, and the float4 read-back of a quarter-warp
                         // (4 rows x 2 halves, or 2 rows x 4 quarters) touches 32 distinct banks
@@ -110,21 +114,28 @@ __device__ __forceinline__ bool stage_tile(WarpScratch& S, const ImgView& im, in
   return nonpos;
 }
 
+// The six axis variants of one BruteHessian in every lane (read back from WarpScratch::geo).
+struct GeoAll {
+  float4 x[3], y[3];  // {a, 1-a, i0 bits, r bits}
+};
+__device__ __forceinline__ int gi(float f) { return __float_as_int(f); }
+
 // General sampling route: `nshift` shifts of the BruteHessian pattern (1 for a template patch),
 // cv::getRectSubPix's border rules per pixel.  "full" 4-tap, "vertical" 2-tap (overflow column, and
 // corners), "horizontal" 2-tap (overflow row): with the unused taps zeroed and A1' = xin ? 1-a : 1,
 // B1' = vert ? 1-b : 1 the weights (A1'B1', aB1', A1'b, ab) reproduce the rule exactly (x*1 is exact
 // and a zero tap adds an exact zero), so one FMA chain serves all pixels.  Results go to S.v.
-__device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im, const AxisGeom& g, int ox, int oy,
+__device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im, int ox, int oy,
                                                int nshift, bool shared_geom, int lane, const PixPack& pix) {
   int toff[SFE_SLOTS];
   unsigned mx[SFE_SLOTS], mv[SFE_SLOTS];  // all-ones where the pixel uses x weights / vertical weights
 #pragma unroll 1
   for (int s = 0; s < nshift; ++s) {
     const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
+    const float4 gx = S.geo[jx], gy = S.geo[jy];  // broadcast loads
     if (s == 0 || !shared_geom) {
-      const int x0 = __shfl_sync(SFE_FULL, g.i0, jx), rx = __shfl_sync(SFE_FULL, g.r, jx);
-      const int y0 = __shfl_sync(SFE_FULL, g.i0, jy), ry = __shfl_sync(SFE_FULL, g.r, jy);
+      const int x0 = gi(gx.z), rx = gi(gx.w);
+      const int y0 = gi(gy.z), ry = gi(gy.w);
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
         const int i = lane + 32 * k;
@@ -140,8 +151,8 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
         mv[k] = (yin || !xin) ? 0xffffffffu : 0u;
       }
     }
-    const float axf = __shfl_sync(SFE_FULL, g.a, jx), ayf = __shfl_sync(SFE_FULL, g.a, jy);
-    const unsigned ax1 = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, jx)), ay1 = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, jy));
+    const float axf = gx.x, ayf = gy.x;
+    const unsigned ax1 = __float_as_uint(gx.y), ay1 = __float_as_uint(gy.y);
     const unsigned one = 0x3f800000u;
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
@@ -160,18 +171,18 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
 // formed ONCE and serve all six shifts, whose weights differ only in which axis variant they take -- 4 loads and the
 // border logic per pixel instead of per pixel and shift.  The loop over the slots is rolled (code size), the six
 // shifts inside are unrolled with compile-time variant indices.
-__device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgView& im, const AxisGeom& g, int ox, int oy,
+__device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgView& im, const GeoAll& G, int ox, int oy,
                                                       int nshift, int lane, const PixPack& pix) {
-  const int x0 = __shfl_sync(SFE_FULL, g.i0, 0), rx = __shfl_sync(SFE_FULL, g.r, 0);
-  const int y0 = __shfl_sync(SFE_FULL, g.i0, 4), ry = __shfl_sync(SFE_FULL, g.r, 4);
+  const int x0 = gi(G.x[0].z), rx = gi(G.x[0].w);
+  const int y0 = gi(G.y[0].z), ry = gi(G.y[0].w);
   float ax[3], ay[3];
   unsigned ax1[3], ay1[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    ax[j] = __shfl_sync(SFE_FULL, g.a, j);
-    ax1[j] = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, j));
-    ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
-    ay1[j] = __float_as_uint(__shfl_sync(SFE_FULL, g.a1, 4 + j));
+    ax[j] = G.x[j].x;
+    ax1[j] = __float_as_uint(G.x[j].y);
+    ay[j] = G.y[j].x;
+    ay1[j] = __float_as_uint(G.y[j].y);
   }
   const unsigned one = 0x3f800000u;
 #pragma unroll 1
@@ -205,7 +216,7 @@ __device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgV
 // Plain route: no border rule and no clipping.  A compact runtime loop re-reads the 4 taps per shift, so it
 // also serves steps in which a +-h shift crosses an integer boundary (the shifts do not share their taps
 // then), template patches (one shift) and footprints that contain a zero.  Results go to S.v.
-__device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& g, int ox, int oy, int nshift, int lane,
+__device__ __forceinline__ void straddle_sample(WarpScratch& S, int ox, int oy, int nshift, int lane,
                                                 const PixPack& pix) {
   int poff[SFE_SLOTS];
 #pragma unroll
@@ -213,9 +224,10 @@ __device__ __forceinline__ void straddle_sample(WarpScratch& S, const AxisGeom& 
 #pragma unroll 1
   for (int s = 0; s < nshift; ++s) {
     const int jx = (SXP >> (2 * s)) & 3, jy = 4 + ((SYP >> (2 * s)) & 3);
-    const int base = (__shfl_sync(SFE_FULL, g.i0, jy) - oy) * TS + (__shfl_sync(SFE_FULL, g.i0, jx) - ox);
-    const float ax = __shfl_sync(SFE_FULL, g.a, jx), ax1 = __shfl_sync(SFE_FULL, g.a1, jx);
-    const float ay = __shfl_sync(SFE_FULL, g.a, jy), ay1 = __shfl_sync(SFE_FULL, g.a1, jy);
+    const float4 gx = S.geo[jx], gy = S.geo[jy];  // broadcast loads
+    const int base = (gi(gy.z) - oy) * TS + (gi(gx.z) - ox);
+    const float ax = gx.x, ax1 = gx.y;
+    const float ay = gy.x, ay1 = gy.y;
     const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
@@ -348,11 +360,23 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     tag.key = key | (np ? 0x80000000u : 0u);
   }
   const bool nonpos = tag.key >> 31;
-  const int ix = __shfl_sync(SFE_FULL, g.i0, 0), iy = __shfl_sync(SFE_FULL, g.i0, 4);
-  const bool mine = (lane & 3) != 3 && lane < 8;
-  const int ibase = __shfl_sync(SFE_FULL, g.i0, lane & 4), rbase = __shfl_sync(SFE_FULL, g.r, lane & 4);
-  const unsigned differ = __ballot_sync(SFE_FULL, mine && (g.i0 != ibase || g.r != rbase));  // shifts do not share taps
-  const unsigned clipped = __ballot_sync(SFE_FULL, mine && g.r != 0);
+  // the eight geometry lanes publish their axis variant; every lane reads all six back (broadcast loads) and derives
+  // the route decisions itself -- no shuffles, no votes
+  if (lane < 8) S.geo[lane] = make_float4(g.a, g.a1, __int_as_float(g.i0), __int_as_float(g.r));
+  __syncwarp();
+  GeoAll G;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    G.x[j] = S.geo[j];
+    G.y[j] = S.geo[4 + j];
+  }
+  const int ix = gi(G.x[0].z), iy = gi(G.y[0].z);
+  // shifts do not share their taps when an origin or a clip count differs from the unshifted variant's
+  const unsigned differ = (unsigned)((gi(G.x[1].z) ^ ix) | (gi(G.x[2].z) ^ ix) | (gi(G.y[1].z) ^ iy) | (gi(G.y[2].z) ^ iy) |
+                                     (gi(G.x[1].w) ^ gi(G.x[0].w)) | (gi(G.x[2].w) ^ gi(G.x[0].w)) |
+                                     (gi(G.y[1].w) ^ gi(G.y[0].w)) | (gi(G.y[2].w) ^ gi(G.y[0].w)));
+  const unsigned clipped0 = (unsigned)(gi(G.x[0].w) | gi(G.y[0].w));  // the unshifted variant (template patches)
+  const unsigned clipped = clipped0 | (unsigned)(gi(G.x[1].w) | gi(G.x[2].w) | gi(G.y[1].w) | gi(G.y[2].w));
   const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
 
   // fast: no border rule, no clipping, all six shifts share their taps, and no pixel can be exactly 0 (a strictly
@@ -360,14 +384,14 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
   // plain: no border rule / clipping for any shift (integer origins within +-1 of the unshifted one).
   const bool zeros = nonpos || clipped != 0;
   const bool fast = !is_tmpl && differ == 0 && !zeros && interior;
-  const bool plain = is_tmpl ? (interior && (clipped & 0x11u) == 0)
+  const bool plain = is_tmpl ? (interior && clipped0 == 0)
                              : (clipped == 0 && ix >= 1 && ix + SFE_PATCH + 1 <= im.w - 1 && iy >= 1 && iy + SFE_PATCH + 1 <= im.h - 1);
   if (!fast) {
     int nshift = is_tmpl ? 1 : 6;
     asm volatile("" : "+r"(nshift));  // opaque: one copy of each loop serves both callers (code size)
-    if (plain) straddle_sample(S, g, ox, oy, nshift, lane, pix);
-    else if (differ == 0) general_sample_shared(S, im, g, ox, oy, nshift, lane, pix);
-    else general_sample(S, im, g, ox, oy, nshift, false, lane, pix);
+    if (plain) straddle_sample(S, ox, oy, nshift, lane, pix);
+    else if (differ == 0) general_sample_shared(S, im, G, ox, oy, nshift, lane, pix);
+    else general_sample(S, im, ox, oy, nshift, false, lane, pix);
   }
 
   if (is_tmpl) {
@@ -395,10 +419,10 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     float ax[3], ax1[3], ay[3], ay1[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      ax[j] = __shfl_sync(SFE_FULL, g.a, j);
-      ax1[j] = __shfl_sync(SFE_FULL, g.a1, j);
-      ay[j] = __shfl_sync(SFE_FULL, g.a, 4 + j);
-      ay1[j] = __shfl_sync(SFE_FULL, g.a1, 4 + j);
+      ax[j] = G.x[j].x;
+      ax1[j] = G.x[j].y;
+      ay[j] = G.y[j].x;
+      ay1[j] = G.y[j].y;
     }
     float t00[SFE_SLOTS], t01[SFE_SLOTS], t10[SFE_SLOTS], t11[SFE_SLOTS];
     const int base = (iy - oy) * TS + (ix - ox);
@@ -455,12 +479,20 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     T[k] = S.T[k * 32 + lane];
     mkT[k] = S.mkT[k * 32 + lane];
   }
+  // lanes 0, 2, .., 10 publish -alpha and -beta of shifts 0..5 ((-v)*alpha == v*(-alpha) and x - beta == x + (-beta), exactly)
+  if (live && !(lane & 1)) {
+    S.ab[lane >> 1] = -alpha_l;
+    S.ab[8 + (lane >> 1)] = -beta_l;
+  }
+  __syncwarp();
   if (!zeros) {
-    const float nalpha_l = -alpha_l, nbeta_l = -beta_l;  // (-v)*alpha == v*(-alpha) and x - beta == x + (-beta), exactly
+    const float4 na03 = *reinterpret_cast<const float4*>(S.ab), nb03 = *reinterpret_cast<const float4*>(S.ab + 8);
+    const float2 na45 = *reinterpret_cast<const float2*>(S.ab + 4), nb45 = *reinterpret_cast<const float2*>(S.ab + 12);
+    const float2 nas[3] = {make_float2(na03.x, na03.y), make_float2(na03.z, na03.w), na45};
+    const float2 nbs[3] = {make_float2(nb03.x, nb03.y), make_float2(nb03.z, nb03.w), nb45};
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-      const float2 na = make_float2(__shfl_sync(SFE_FULL, nalpha_l, 4 * p), __shfl_sync(SFE_FULL, nalpha_l, 4 * p + 2));
-      const float2 nb = make_float2(__shfl_sync(SFE_FULL, nbeta_l, 4 * p), __shfl_sync(SFE_FULL, nbeta_l, 4 * p + 2));
+      const float2 na = nas[p], nb = nbs[p];
       float2 acc = both(0.f);
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:133-139; template zeros are folded into mkT
@@ -477,7 +509,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     for (int j = 0; j < 6; ++j) part[j] = 0.f;
 #pragma unroll 1
     for (int s = 0; s < 6; ++s) {
-      const float alpha = __shfl_sync(SFE_FULL, alpha_l, 2 * s), beta = __shfl_sync(SFE_FULL, beta_l, 2 * s);
+      const float alpha = -S.ab[s], beta = -S.ab[8 + s];
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
