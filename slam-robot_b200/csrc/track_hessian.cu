@@ -377,7 +377,8 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
                                      (gi(G.y[1].w) ^ gi(G.y[0].w)) | (gi(G.y[2].w) ^ gi(G.y[0].w)));
   const unsigned clipped0 = (unsigned)(gi(G.x[0].w) | gi(G.y[0].w));  // the unshifted variant (template patches)
   const unsigned clipped = clipped0 | (unsigned)(gi(G.x[1].w) | gi(G.x[2].w) | gi(G.y[1].w) | gi(G.y[2].w));
-  const bool interior = ix >= 0 && ix + SFE_PATCH <= im.w - 1 && iy >= 0 && iy + SFE_PATCH <= im.h - 1;
+  // 0 <= ix <= w - 14 as one unsigned compare per axis (a level narrower than the patch makes the bound 0: never true)
+  const bool interior = (unsigned)ix < (unsigned)max(im.w - SFE_PATCH, 0) && (unsigned)iy < (unsigned)max(im.h - SFE_PATCH, 0);
 
   // fast: no border rule, no clipping, all six shifts share their taps, and no pixel can be exactly 0 (a strictly
   // positive footprint under positive weights that sum to 1) -- patch values stay in registers.
@@ -385,7 +386,8 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
   const bool zeros = nonpos || clipped != 0;
   const bool fast = !is_tmpl && differ == 0 && !zeros && interior;
   const bool plain = is_tmpl ? (interior && clipped0 == 0)
-                             : (clipped == 0 && ix >= 1 && ix + SFE_PATCH + 1 <= im.w - 1 && iy >= 1 && iy + SFE_PATCH + 1 <= im.h - 1);
+                             : (clipped == 0 && (unsigned)(ix - 1) < (unsigned)max(im.w - SFE_PATCH - 2, 0) &&
+                                (unsigned)(iy - 1) < (unsigned)max(im.h - SFE_PATCH - 2, 0));  // 1 <= ix <= w - 15
   if (!fast) {
     int nshift = is_tmpl ? 1 : 6;
     asm volatile("" : "+r"(nshift));  // opaque: one copy of each loop serves both callers (code size)
@@ -550,11 +552,12 @@ __device__ __forceinline__ int track_feature(WarpScratch& S, TileTag& tag, const
     Tmpl t;
     t.mean = t.sumsq = 0.f;
     const ImgView tim = img_of(tp, 0, i, tframe), sim = img_of(sp, 0, i, sframe);
+    const float wf = (float)sim.w, hf = (float)sim.h;
     // it == -1 extracts the template patch of this level (GetPatches); it >= 0 are the Newton steps
 #pragma unroll 1
     for (int it = -1; it < maxit; ++it) {
       const bool is_tmpl = it < 0;
-      if (!is_tmpl && (px < margin || py < margin || (px + margin) > (float)sim.w || (py + margin) > (float)sim.h))
+      if (!is_tmpl && (px < margin || py < margin || (px + margin) > wf || (py + margin) > hf))
         return SFE_OUT_OF_BOUNDS;
       ImgView im;
       im.p = is_tmpl ? tim.p : sim.p;
