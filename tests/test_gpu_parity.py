@@ -502,6 +502,23 @@ def test_hamming_extreme_rows_bit_exact(fe, po, synth, hamming_kernel):
     assert (i2 == np.array([0, 1])).all() and (d2 == 256).all()
 
 
+def test_hamming_random_shapes_bit_exact(fe, po, synth, hamming_kernel):
+    """Randomly drawn problem shapes: partial query tiles, partial train tiles, one to many train splits per query tile
+    (few queries against a long train set puts every SM on its own slice of the train rows), batches -- each against
+    the oracle, for both kernels."""
+    rng = np.random.default_rng(2026)
+    shapes = [(int(rng.integers(1, 700)), int(rng.integers(1, 3000)), int(rng.integers(1, 5))) for _ in range(10)]
+    shapes += [(100, 100000, 1), (3, 40000, 2), (1000, 7, 3), (257, 511, 1)]
+    for nq, nt, batch in shapes:
+        t = synth.make_descriptors(nq + 7 * nt, nt * batch, dup_frac=0.05)
+        q = synth.make_descriptors(nq * 3 + nt, nq * batch, dup_frac=0.3, source=t)
+        idx, dist, ok = fe.match_hamming256(q, t, 4, 5, 80, batch=batch)
+        for b in range(batch):
+            oi, od, oo = po.hamming256_top2(q[b * nq:(b + 1) * nq], t[b * nt:(b + 1) * nt], 4, 5, 80)
+            sl = slice(b * nq, (b + 1) * nq)
+            assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od) and np.array_equal(ok[sl], oo), (nq, nt, batch, b)
+
+
 def test_config5_hamming_1m_x_1m_properties(fe, po, synth, hamming_kernel):
     """BASELINE config 5 at full size on one GPU (10^12 comparisons): the oracle cannot finish that, so the result is
     checked through size-independent properties -- planted duplicates are found at distance 0 at the LOWEST train index
