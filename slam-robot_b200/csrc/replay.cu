@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 struct sfe_replay {
@@ -185,7 +187,8 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
   // chunk size: default = an eighth of the batch (at least 8 pairs so that the kernels still fill the GPU; measured
   // best on B200 for 128 and 512 VGA pairs) but at most 128 pairs -- three pyramid sets and two staging buffers of
   // 2 * chunk frames each are 1.4 GB then, whatever the length of the replay; the first chunk is a quarter of
-  // that, so compute starts after a short upload
+  // that and the second a half, so compute starts after a short upload and each upload (54 GB/s measured) stays ahead
+  // of the tracking of the chunk before it (tracking a pair takes 2.75x its upload)
   int chunk = chunk_pairs > 0 ? chunk_pairs : (npairs + 7) / 8;
   if (chunk_pairs <= 0 && chunk < 8) chunk = 8;
   if (chunk_pairs <= 0 && chunk > 128) chunk = 128;
@@ -198,24 +201,32 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
   sfe_replay* r = ctx->replay;
   cudaStream_t cs0 = ctx->stream, xs = r->copy_stream, os = r->out_stream, ps = r->pyr_stream;
 
+  // SFE_REPLAY_TRACE=1 (diagnostics): per-chunk event times of the pipeline on stderr
+  static const bool trace = getenv("SFE_REPLAY_TRACE") != nullptr;
+  constexpr int TRACE_MAX = 64;
+  cudaEvent_t tr_ev[TRACE_MAX][5];
+  cudaEvent_t tr_t0 = nullptr;
+  int tr_n = 0;
+  if (trace) {
+    cudaEventCreate(&tr_t0);
+    cudaEventRecord(tr_t0, cs0);
+  }
   // the other streams must not run ahead of whatever the caller queued on the context's stream before this call
   // (which also covers the staging buffers of a previous call)
   RCU(cudaEventRecord(r->drained, cs0));
   RCU(cudaStreamWaitEvent(xs, r->drained, 0));
   RCU(cudaStreamWaitEvent(os, r->drained, 0));
   RCU(cudaStreamWaitEvent(ps, r->drained, 0));
-  // the feature lists are small: upload them in one piece on the context's stream, while the copy stream already
-  // brings in the first chunk's frames; the second compute stream waits for them through `drained` re-recorded below
-  RCU(cudaMemcpyAsync(r->d_from, from_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
-  RCU(cudaMemcpyAsync(r->d_to, to_xy, 8 * n, cudaMemcpyHostToDevice, cs0));
-  if (levels) RCU(cudaMemcpyAsync(r->d_lv, levels, 4 * n, cudaMemcpyHostToDevice, cs0));
-  RCU(cudaEventRecord(r->drained, cs0));
+  // the feature lists travel with their chunk on the copy stream (slices of a few hundred KB in front of the chunk's
+  // frames).  Round 1 uploaded them in one piece on the context's stream: measured with SFE_REPLAY_TRACE, everything
+  // queued on that stream behind those copies -- the first chunk's tracker -- then waited until the copy engine had
+  // drained the first four frame uploads (1.2 ms of a 29 ms call).  The compute streams carry no copy-engine work now.
   RCU(cudaStreamWaitEvent(r->compute2, r->drained, 0));
-
   const size_t dense_frame = (size_t)3 * w * h;
   int p0 = 0;
   for (int k = 0; p0 < npairs; ++k) {
-    const int b = k & 1, set = k % 3, want = k == 0 ? first_chunk : chunk, c = npairs - p0 < want ? npairs - p0 : want;
+    const int b = k & 1, set = k % 3, want = k == 0 ? first_chunk : (k == 1 && 2 * first_chunk < chunk ? 2 * first_chunk : chunk),
+              c = npairs - p0 < want ? npairs - p0 : want;
     cudaStream_t cs = b ? r->compute2 : cs0;
     // ---- copy stream: frames of chunk k into staging buffer b (free once chunk k-2's pyramids are built)
     if (k >= 2) RCU(cudaStreamWaitEvent(xs, r->consumed[b], 0));
@@ -223,6 +234,12 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     const int nbuild = seq_stride ? c + seq_stride : 2 * c, to_first = seq_stride ? seq_stride : c;
     uint8_t* up = yuyv ? r->d_raw[b] : r->d_frames[b];
     const size_t up_frame = (size_t)bpp * w * h;
+    {
+      const size_t f0 = (size_t)p0 * n_per_pair, nf = (size_t)c * n_per_pair;
+      RCU(cudaMemcpyAsync(r->d_from + 2 * f0, from_xy + 2 * f0, 8 * nf, cudaMemcpyHostToDevice, xs));
+      RCU(cudaMemcpyAsync(r->d_to + 2 * f0, to_xy + 2 * f0, 8 * nf, cudaMemcpyHostToDevice, xs));
+      if (levels) RCU(cudaMemcpyAsync(r->d_lv + f0, levels + f0, 4 * nf, cudaMemcpyHostToDevice, xs));
+    }
     rc = upload_frames(ctx, up, from_bgr + (size_t)p0 * frame_stride, w, h, row_stride, frame_stride,
                        seq_stride ? nbuild : c, xs, bpp);
     if (!rc && !seq_stride)
@@ -230,6 +247,12 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
                          row_stride, frame_stride, c, xs, bpp);
     if (rc) return rc;
     RCU(cudaEventRecord(r->copied[b], xs));
+    const bool tr = trace && k < TRACE_MAX;
+    if (tr) {
+      for (int e = 0; e < 5; ++e) cudaEventCreate(&tr_ev[k][e]);
+      cudaEventRecord(tr_ev[k][0], xs);
+      tr_n = k + 1;
+    }
     // ---- pyramid stream: the pyramids of the chunk's frames into set k % 3 (free once chunk k-3 has been tracked)
     RCU(cudaStreamWaitEvent(ps, r->copied[b], 0));
     if (k >= 3) RCU(cudaStreamWaitEvent(ps, r->tracked[set], 0));
@@ -244,8 +267,10 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     ctx->launches += nl;
     RCU(cudaEventRecord(r->consumed[b], ps));
     RCU(cudaEventRecord(r->built[set], ps));
+    if (tr) cudaEventRecord(tr_ev[k][1], ps);
     // ---- compute stream b: forward/backward tracking of the chunk's features (the work-queue counter is per stream)
     RCU(cudaStreamWaitEvent(cs, r->built[set], 0));
+    if (tr) cudaEventRecord(tr_ev[k][2], cs);
     const size_t f0 = (size_t)p0 * n_per_pair;
     const int nf = c * n_per_pair;
     TrackArgs ta{nf, n_per_pair, 0, to_first, r->d_from + 2 * f0, r->d_to + 2 * f0, levels ? r->d_lv + f0 : nullptr, default_levels,
@@ -254,6 +279,7 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     if (nl < 0) return rfail(ctx, SFE_ERR_CUDA, "track launch", (cudaError_t)(-nl));
     ctx->launches += nl;
     RCU(cudaEventRecord(r->tracked[set], cs));
+    if (tr) cudaEventRecord(tr_ev[k][3], cs);
     // ---- output stream: results of chunk k back to the caller's buffers
     RCU(cudaStreamWaitEvent(os, r->tracked[set], 0));
     RCU(cudaMemcpyAsync(to_xy + 2 * f0, r->d_to + 2 * f0, 8 * (size_t)nf, cudaMemcpyDeviceToHost, os));
@@ -262,6 +288,7 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
     if (status_bwd) RCU(cudaMemcpyAsync(status_bwd + f0, r->d_s2 + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (accepted) RCU(cudaMemcpyAsync(accepted + f0, r->d_acc + f0, (size_t)nf, cudaMemcpyDeviceToHost, os));
     if (steps) RCU(cudaMemcpyAsync(steps + f0, r->d_steps + f0, 4 * (size_t)nf, cudaMemcpyDeviceToHost, os));
+    if (tr) cudaEventRecord(tr_ev[k][4], os);
     p0 += c;
   }
   cudaStream_t cs = cs0;
@@ -269,6 +296,19 @@ int replay_run(sfe_ctx* ctx, int w, int h, int depth, int npairs, int seq_stride
   RCU(cudaEventRecord(r->drained, os));
   RCU(cudaStreamWaitEvent(cs, r->drained, 0));
   RCU(cudaStreamSynchronize(cs));
+  if (trace) {
+    fprintf(stderr, "replay trace (ms after the call's first stream operation): chunk: copied built track_start tracked downloaded\n");
+
+    for (int k = 0; k < tr_n; ++k) {
+      float t[5];
+      for (int e = 0; e < 5; ++e) {
+        cudaEventElapsedTime(&t[e], tr_t0, tr_ev[k][e]);
+        cudaEventDestroy(tr_ev[k][e]);
+      }
+      fprintf(stderr, "  %2d: %7.3f %7.3f %7.3f %7.3f %7.3f\n", k, t[0], t[1], t[2], t[3], t[4]);
+    }
+    cudaEventDestroy(tr_t0);
+  }
   return SFE_SUCCESS;
 }
 }  // namespace
