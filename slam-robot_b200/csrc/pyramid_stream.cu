@@ -530,8 +530,14 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
   auto ok_level = [](int w, int h) { return w % 8 == 0 && w >= 16 && h >= 16; };
   if (v.depth < 2 || !ok_level(v.w[0], v.h[0]) || ((uintptr_t)bgr & 3) || row_stride % 4 || frame_stride % 4) return 0;
   int built = 0;
+  // A strip warp walks its rows serially, so a level with little work per launch -- the deeper levels of ONE live frame --
+  // is latency-bound on this kernel (measured, one VGA frame: 11 us per level against 5 us on the tiled kernel, which
+  // covers the level with many small CTAs).  Levels >= 2 below this many output pixels per launch are left to the caller's
+  // tiled kernels; both kernels are bit-identical to the oracle.
+  static const long long tiled_below = getenv("SFE_PYR_TILED_BELOW") ? atoll(getenv("SFE_PYR_TILED_BELOW")) : 160 * 120 * 8;
   for (int l = 1; l < v.depth; ++l) {
     if (!ok_level(v.w[l - 1], v.h[l - 1])) break;
+    if (l >= 2 && (long long)count * v.w[l] * v.h[l] < tiled_below) break;
     StreamArgs a{};
     a.w = v.w[l - 1]; a.h = v.h[l - 1]; a.w1 = v.w[l]; a.h1 = v.h[l];
     a.hbody = pd_hbody(a.w);
