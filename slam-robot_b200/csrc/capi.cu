@@ -702,9 +702,16 @@ int gftt_cap(int w, int h) {  // candidate capacity per frame: a power of two (t
   while (cap < ((w + 1) / 2) * ((h + 1) / 2)) cap <<= 1;
   return cap;
 }
+// Up to this many frames per call take the two-pass response kernels (gftt.cu): the live robot's keyframe, not a batch.
+// SFE_GFTT_TWO_PASS=0 / =N (experiments, tests) moves the limit.
+int gftt_two_pass_limit() {
+  static const int v = getenv("SFE_GFTT_TWO_PASS") ? atoi(getenv("SFE_GFTT_TWO_PASS")) : 4;
+  return v;
+}
 size_t gftt_ws_bytes(int w, int h, int count) {
   return padded(sizeof(float) * (size_t)w * h * count) + 2 * padded(sizeof(int) * (size_t)count) +
-         padded(sizeof(unsigned long long) * (size_t)gftt_cap(w, h) * count);
+         padded(sizeof(unsigned long long) * (size_t)gftt_cap(w, h) * count) +
+         (count <= gftt_two_pass_limit() ? padded((sizeof(double) + sizeof(float)) * 3 * (size_t)w * h * count) : 0);
 }
 int gftt_run(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stride, size_t frame_stride, int count,
              int max_corners, double quality, double min_distance, float* corners_dev, int32_t* ncorners_dev, float** eig_dev) {
@@ -723,10 +730,12 @@ int gftt_run(sfe_ctx* ctx, const uint8_t* bgr_dev, int w, int h, size_t row_stri
   unsigned* mx = c.take<unsigned>(count);
   int* nc = c.take<int>(count);
   unsigned long long* keys = c.take<unsigned long long>((size_t)gftt_cap(w, h) * count);
+  // row sums (doubles) and, right behind them, box sums (floats) of the few-frame path
+  double* rowsums = count <= gftt_two_pass_limit() ? (double*)c.take<char>((sizeof(double) + sizeof(float)) * 3 * (size_t)w * h * count) : nullptr;
   if (eig_dev) *eig_dev = eig;
   return launched(ctx,
                   launch_good_features(bgr_dev, row_stride, frame_stride, w, h, count, max_corners, quality, min_distance, eig, mx,
-                                       nc, keys, gftt_cap(w, h), corners_dev, ncorners_dev, ctx->stream),
+                                       nc, keys, gftt_cap(w, h), corners_dev, ncorners_dev, rowsums, ctx->stream),
                   "good_features launch: %s");
 }
 bool gftt_args_ok(int w, int h, size_t row_stride, int count, int max_corners, double quality, double min_distance) {

@@ -154,6 +154,132 @@ __global__ void __launch_bounds__(32) gftt_eig_kernel(const EigArgs a) {
   if (lane == 0) atomicMax(a.max_code + frame, order_code(vmax));
 }
 
+// ---- the same response map for a FEW frames (a keyframe of the live robot) -------------------------------------------
+// gftt_eig_kernel walks each 28-column strip down the rows in one warp: right for a batch (one pass, everything in
+// registers), but for one VGA frame that is 23 warps taking 482 serial row steps -- 224 us.  The only part that has to be
+// serial is the running column sum; everything before it is independent per pixel.  So for small batches:
+//   gftt_rowsum_kernel   tiled, one thread per pixel: gray -> Sobel row parts -> covariance products -> the three
+//                        horizontal 3-sums R(y, x) in double, stored (24 bytes per pixel);
+//   gftt_colsum_kernel   one thread per column and channel: S += R(y+1); box = (float)S; S -= R(y-1) down the rows -- two
+//                        dependent double additions per row;
+//   gftt_eigval_kernel   per pixel: the eigenvalue from the three box sums, and the frame maximum.
+// Operation for operation what gftt_eig_kernel computes (same border rules, same order of the double additions), so
+// the response maps are bit-identical; tests run both.
+constexpr int RS_TW = 32, RS_TH = 8;
+
+__global__ void __launch_bounds__(RS_TW * RS_TH) gftt_rowsum_kernel(const EigArgs a, double* __restrict__ R /* [count][3][h][w] */) {
+  __shared__ float G[RS_TH + 2][RS_TW + 4];   // gray, rows y0-1 .. y0+TH (reflected), columns x0-2 .. x0+TW+1 (clamped)
+  __shared__ float Pr[RS_TH + 2][RS_TW + 2];  // Sobel row parts at columns x0-1 .. x0+TW
+  __shared__ float Pq[RS_TH + 2][RS_TW + 2];
+  __shared__ float C[3][RS_TH][RS_TW + 2];    // covariance products at columns x0-1 .. x0+TW
+  const int frame = blockIdx.z, x0 = blockIdx.x * RS_TW, y0 = blockIdx.y * RS_TH, tid = threadIdx.x;
+  const uint8_t* src = a.bgr + (size_t)frame * a.frame_stride;
+  const double sd = 1.0 / (4.0 * 3.0 * 255.0);
+  const float k0 = (float)sd, k1 = (float)(2.0 * sd);
+  for (int e = tid; e < (RS_TH + 2) * (RS_TW + 4); e += RS_TW * RS_TH) {
+    const int i = e / (RS_TW + 4), j = e % (RS_TW + 4);
+    int y = y0 - 1 + i;
+    y = y < 0 ? -y : y;
+    y = y >= a.h ? 2 * (a.h - 1) - y : y;
+    y = min(max(y, 0), a.h - 1);                       // rows past the reflection belong to pixels outside the image
+    const int x = min(max(x0 - 2 + j, 0), a.w - 1);
+    const uint8_t* p = src + (size_t)y * a.row_stride + 3 * (size_t)x;
+    G[i][j] = (float)((9798 * (int)__ldg(p) + 19235 * (int)__ldg(p + 1) + 3735 * (int)__ldg(p + 2) + (1 << 14)) >> 15);
+  }
+  __syncthreads();
+  for (int e = tid; e < (RS_TH + 2) * (RS_TW + 2); e += RS_TW * RS_TH) {
+    const int i = e / (RS_TW + 2), j = e % (RS_TW + 2), X = x0 - 1 + j;
+    float gl = G[i][j], gr = G[i][j + 2];
+    const float g = G[i][j + 1];
+    if (X == 0) gl = gr;             // BORDER_REFLECT_101: g(-1) = g(1)
+    if (X == a.w - 1) gr = gl;       //                     g(w) = g(w-2)
+    Pr[i][j] = gr - gl;
+    Pq[i][j] = fmaf(gr, k0, fmaf(g, k1, gl * k0));
+  }
+  __syncthreads();
+  for (int e = tid; e < RS_TH * (RS_TW + 2); e += RS_TW * RS_TH) {
+    const int i = e / (RS_TW + 2), j = e % (RS_TW + 2);
+    const float dx = fmaf(Pr[i][j] + Pr[i + 2][j], k0, Pr[i + 1][j] * k1);
+    const float dy = Pq[i + 2][j] - Pq[i][j];
+    C[0][i][j] = dx * dx;
+    C[1][i][j] = dx * dy;
+    C[2][i][j] = dy * dy;
+  }
+  __syncthreads();
+  const int i = tid / RS_TW, j = tid % RS_TW, X = x0 + j, Y = y0 + i;
+  if (X < a.w && Y < a.h) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float cl = C[ch][i][j], cr = C[ch][i][j + 2];
+      const float c = C[ch][i][j + 1];
+      if (X == 0) cl = cr;
+      if (X == a.w - 1) cr = cl;
+      R[(((size_t)frame * 3 + ch) * a.h + Y) * a.w + X] = __dadd_rn(__dadd_rn((double)cl, (double)c), (double)cr);
+    }
+  }
+}
+
+// One thread per (column, covariance channel): the three running sums of a pixel are independent chains, so they run in
+// three threads (60 warps per VGA frame instead of 20, a third of the instructions per row each).
+__global__ void __launch_bounds__(128) gftt_colsum_kernel(const EigArgs a, const double* __restrict__ R, float* __restrict__ box /* [count][3][h][w] */) {
+  const int frame = blockIdx.z, ch = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= a.w) return;
+  const size_t plane = (size_t)a.h * a.w;
+  const double* r = R + ((size_t)frame * 3 + ch) * plane + x;
+  float* out = box + ((size_t)frame * 3 + ch) * plane + x;
+  auto row = [&](int y) -> double {         // R(y) with R(-1) = R(1) and R(h) = R(h-2)
+    y = y < 0 ? -y : y;
+    y = y >= a.h ? 2 * (a.h - 1) - y : y;
+    return __ldg(r + (size_t)y * a.w);
+  };
+  constexpr int AHEAD = 16;                 // rows requested ahead of the running sum
+  double nxt[AHEAD];
+  double prev = row(-1), cur = row(0);
+  double S = __dadd_rn(__dadd_rn(0.0, prev), cur);   // (0 + R(-1)) + R(0)
+#pragma unroll
+  for (int u = 0; u < AHEAD; ++u) nxt[u] = row(1 + u);
+#pragma unroll 1
+  for (int yb = 0; yb < a.h; yb += AHEAD) {
+#pragma unroll
+    for (int u = 0; u < AHEAD; ++u) {
+      const int y = yb + u;
+      if (y >= a.h) break;
+      const double rp = nxt[u];             // R(y+1)
+      nxt[u] = row(y + 1 + AHEAD);
+      const double s = __dadd_rn(S, rp);
+      out[(size_t)y * a.w] = (float)s;
+      S = __dsub_rn(s, prev);               // minus R(y-1)
+      prev = cur;
+      cur = rp;
+    }
+  }
+}
+
+// Min eigenvalue of the 2x2 box-summed covariance (corner.cpp calcMinEigenVal) and the frame maximum.
+__global__ void __launch_bounds__(256) gftt_eigval_kernel(const EigArgs a, const float* __restrict__ box) {
+  const int frame = blockIdx.y;
+  const size_t plane = (size_t)a.h * a.w, i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  float e = -3.0e38f;
+  if (i < plane) {
+    const float* b = box + (size_t)frame * 3 * plane + i;
+    const float aa = b[0] * 0.5f, bb = b[plane], cc = b[2 * plane] * 0.5f;
+    const float t = aa - cc;
+    e = (aa + cc) - sqrtf(t * t + bb * bb);
+    a.eig[(size_t)frame * plane + i] = e;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) e = fmaxf(e, __shfl_xor_sync(SFE_FULL, e, o));
+  __shared__ float wmax[8];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = wmax[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
+    atomicMax(a.max_code + frame, order_code(m));
+  }
+}
+
 struct NmsArgs {
   const float* eig;
   const unsigned* max_code;
@@ -234,29 +360,51 @@ __device__ __forceinline__ void bitonic_chunk(unsigned long long* sk, int chunk_
 }
 
 // Greedy minimum-distance selection (featureselect.cpp) over the first `n` keys of the descending list `list`: a
-// candidate is kept unless an accepted corner lies closer than min_distance.  Sequential by nature; warp 0 walks the
-// candidates and tests each against the accepted corners 32 at a time.  Returns the number of corners (in every lane).
+// candidate is kept unless an accepted corner lies closer than min_distance.  Sequential in the accepted corners only;
+// warp 0 does it.  Returns the number of corners (in every lane).
 __device__ __forceinline__ int greedy_select(const SelArgs& a, const unsigned long long* list, int n, float* acc, float* out, int lane) {
   const bool check = a.min_distance >= 1.0;
   const double md2 = a.min_distance * a.min_distance;
   int cnt = 0;
-  for (int c = 0; c < n && cnt < a.max_corners; ++c) {
-    const unsigned ofs = (unsigned)list[c];
-    const int y = ofs / a.w, x = ofs - y * a.w;
-    bool bad = false;
-    if (check)
-      for (int k = lane; k < cnt; k += 32) {
-        const float dx = (float)x - acc[2 * k], dy = (float)y - acc[2 * k + 1];
+  // 32 candidates at a time, one per lane.  First every lane tests its candidate against the corners accepted in earlier
+  // batches (no dependency between lanes); then the survivors are settled in list order: the first one is accepted, the
+  // later ones test against it, and so on -- one round per ACCEPTED corner instead of one per candidate (round 1 walked
+  // the ~1000 candidates of a frame one by one: 75 of the 95 us of a keyframe's selection).
+  for (int c0 = 0; c0 < n && cnt < a.max_corners; c0 += 32) {
+    const int c = c0 + lane;
+    bool alive = c < n;
+    float fx = 0.f, fy = 0.f;
+    if (alive) {
+      const unsigned ofs = (unsigned)list[c];
+      const int y = ofs / a.w, x = ofs - y * a.w;
+      fx = (float)x;
+      fy = (float)y;
+    }
+    if (check && alive) {
+      bool bad = false;
+      for (int k = 0; k < cnt; ++k) {
+        const float dx = fx - acc[2 * k], dy = fy - acc[2 * k + 1];
         bad |= (double)(dx * dx + dy * dy) < md2;
       }
-    if (__any_sync(SFE_FULL, bad)) continue;
-    if (lane == 0) {
-      acc[2 * cnt] = (float)x;
-      acc[2 * cnt + 1] = (float)y;
-      out[2 * cnt] = (float)x;
-      out[2 * cnt + 1] = (float)y;
+      alive = !bad;
     }
-    ++cnt;
+    unsigned m = __ballot_sync(SFE_FULL, alive);
+    while (m != 0u && cnt < a.max_corners) {
+      const int j = __ffs(m) - 1;
+      const float jx = __shfl_sync(SFE_FULL, fx, j), jy = __shfl_sync(SFE_FULL, fy, j);
+      if (lane == j) {
+        acc[2 * cnt] = fx;
+        acc[2 * cnt + 1] = fy;
+        out[2 * cnt] = fx;
+        out[2 * cnt + 1] = fy;
+      }
+      ++cnt;
+      if (check && alive && lane > j) {
+        const float dx = fx - jx, dy = fy - jy;
+        if ((double)(dx * dx + dy * dy) < md2) alive = false;
+      }
+      m = __ballot_sync(SFE_FULL, alive && lane > j);
+    }
     __syncwarp();
   }
   return cnt;
@@ -386,16 +534,27 @@ __global__ void __launch_bounds__(SEL_THREADS) gftt_select_kernel(const SelArgs 
 
 }  // namespace
 
-// Enqueues the three kernels for `count` frames.  Workspace (device): eig [count*w*h] floats, max_code [count],
-// ncand [count], keys [count*cap].  Returns the number of launches or a negative cudaError.
+// Enqueues the kernels for `count` frames.  Workspace (device): eig [count*w*h] floats, max_code [count],
+// ncand [count], keys [count*cap], rowsums [count*3*h*w] doubles followed by as many floats, or NULL (selects the
+// one-pass response kernel).
+// Returns the number of launches or a negative cudaError.
 int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_stride, int w, int h, int count, int max_corners,
                          double quality, double min_distance, float* eig, unsigned* max_code, int* ncand,
-                         unsigned long long* keys, int cap, float* corners, int* ncorners, cudaStream_t s) {
+                         unsigned long long* keys, int cap, float* corners, int* ncorners, double* rowsums, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(max_code, 0, sizeof(unsigned) * count, s);
   if (e == cudaSuccess) e = cudaMemsetAsync(ncand, 0, sizeof(int) * count, s);
   if (e != cudaSuccess) return -(int)e;
   EigArgs ea{bgr, row_stride, frame_stride, eig, max_code, w, h, (w + EIG_USEFUL - 1) / EIG_USEFUL};
-  gftt_eig_kernel<<<ea.strips * count, 32, 0, s>>>(ea);
+  int launches = 3;
+  if (rowsums && h >= 3) {  // a few frames: the two-pass form (the caller provides 24 bytes per pixel of workspace for it)
+    gftt_rowsum_kernel<<<dim3((w + RS_TW - 1) / RS_TW, (h + RS_TH - 1) / RS_TH, count), RS_TW * RS_TH, 0, s>>>(ea, rowsums);
+    float* box = reinterpret_cast<float*>(rowsums + 3 * (size_t)w * h * count);   // the caller's workspace holds both
+    gftt_colsum_kernel<<<dim3((w + 127) / 128, 3, count), 128, 0, s>>>(ea, rowsums, box);
+    gftt_eigval_kernel<<<dim3((unsigned)(((size_t)w * h + 255) / 256), count), 256, 0, s>>>(ea, box);
+    launches = 5;
+  } else {
+    gftt_eig_kernel<<<ea.strips * count, 32, 0, s>>>(ea);
+  }
   NmsArgs na{eig, max_code, keys, ncand, w, h, cap, quality};
   gftt_nms_kernel<<<dim3((w + 255) / 256, (h + NMS_ROWS - 1) / NMS_ROWS, count), 256, 0, s>>>(na);
   SelArgs sa{keys, ncand, corners, ncorners, w, cap, max_corners, min_distance};
@@ -407,5 +566,5 @@ int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_str
   }
   gftt_select_kernel<<<count, SEL_THREADS, smem, s>>>(sa);
   e = cudaGetLastError();
-  return e == cudaSuccess ? 3 : -(int)e;
+  return e == cudaSuccess ? launches : -(int)e;
 }

@@ -135,7 +135,7 @@ int launch_hamming256(const uint32_t* q, int nq, const uint32_t* t, int nt, int 
                       void** ws, size_t* ws_cap, cudaStream_t s);
 int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_stride, int w, int h, int count, int max_corners,
                          double quality, double min_distance, float* eig, unsigned* max_code, int* ncand,
-                         unsigned long long* keys, int cap, float* corners, int* ncorners, cudaStream_t s);
+                         unsigned long long* keys, int cap, float* corners, int* ncorners, double* rowsums, cudaStream_t s);
 int launch_seed_features(int n, const double* points4, const double* uncertainty, const double* rot, const double* trans,
                          const double* k, const float* from_xy, int cols, int rows, float* seed_xy, int32_t* levels,
                          uint8_t* go, cudaStream_t s);
