@@ -5,21 +5,23 @@
 // t' = 1 - 2*tbit,  sum_k q'_k t'_k = 256 - 2 d.  The query tile is unpacked to a_k = -8 q'_k, the train tile to
 // b_k = +8 t'_k (signed bytes), so  sum_k a_k b_k = 128 d - 2^14  -- every partial sum is an integer of at most 15 bits,
 // s32 accumulation is exact, there is no rounding anywhere.  One more K block carries the tie rule: a = (1, 0, ...),
-// b = (j mod 128, 0, ...) with j the train row's index inside its 256-row tile, so the accumulator the tensor core
+// b = (j, 0, ...) with j the train row's index inside its 128-row tile, so the accumulator the tensor core
 // hands back is
-//        acc[i][j] = 128 d(i,j) + (j mod 128) - 16384        in [-16384, 16511]: a signed 16-bit number
-// which orders the 128 columns a thread scans by (distance, train index) -- exactly the packed key of hamming.cu
+//        acc[i][j] = 128 d(i,j) + j - 16384        in [-16384, 16511]: a signed 16-bit number
+// which orders the columns of a tile by (distance, train index) -- exactly the packed key of hamming.cu
 // (lowest train index wins ties, cv2.BFMatcher's rule; oracle.c orc_hamming256_top2).  Because the key fits 16 bits,
 // tcgen05.ld.pack::16b delivers TWO columns per register and the scan is a running two-smallest in both halves of a
 // register at once (VIMNMX.S16x2 / VIMNMX3.S16x2: 5 instructions per FOUR columns, no decode, no index arithmetic); the
 // winners of a tile are decoded once per tile into the global keys dist << 22 | index.
 //
-// Roles (544 threads, one CTA per SM, persistent over (batch, 128-query tile, train split) items):
-//   warps 0-15 unpack the next 256-row train tile (bits -> signed bytes, shared memory in the no-swizzle K-major
+// Roles (544 threads, one CTA per SM, persistent over (batch, 256-query tile, train split) items):
+//   warps 0-15 unpack the next 128-row train tile (bits -> signed bytes, shared memory in the no-swizzle K-major
 //              core-matrix layout the MMA descriptors name), then scan the previous tile's accumulators: warp w reads
-//              TMEM lanes 32 (w % 4).. with tcgen05.ld -- one query row per thread -- columns 64 (w / 4)..
-//   warp 16    waits for a full stage, issues 9 x tcgen05.mma (M 128, N 256, K 32) into one half of the 512 TMEM
-//              columns and commits them to the stage's mbarrier.
+//              TMEM lanes 32 (w % 4).. of query half (w / 4) % 2 with tcgen05.ld -- one query row per thread --
+//              columns 64 (w / 8)..
+//   warp 16    waits for a full stage, issues 2 x 9 tcgen05.mma (M 128, N 128, K 32: the item's two 128-query blocks
+//              against the same train tile) into two of the four 128-column accumulators and commits them to the stage's
+//              mbarrier.  Two query blocks per train tile halve the unpack work per comparison.
 // The train stages, the accumulators and the query tile are double-buffered, so the tensor core works on tile g
 // while the workers scan tile g-1 and unpack tile g+1, across item boundaries as well.  What bounds it is the ALU pipe
 // of the worker warps (profiles/ham_r2*): the nine UTCIMMA per tile hide completely behind unpack + scan.
@@ -27,24 +29,20 @@
 
 namespace {
 
-constexpr int MM_M = 128;            // queries per item (TMEM lanes)
-constexpr int MM_N = 256;            // train rows per tile (TMEM columns of one accumulator)
+constexpr int MM_M = 128;            // rows of one MMA (TMEM lanes)
+constexpr int MM_MQ = 256;           // queries per item: two MMA row blocks share every train tile (halves the unpack per comparison)
+constexpr int MM_N = 128;            // train rows per tile (TMEM columns of one accumulator)
 constexpr int MM_KB = 9;             // K blocks of 32 bytes: 8 x 32 descriptor bits + the index block
-#ifndef MM_PARTS_D
-#define MM_PARTS_D 4
-#endif
-constexpr int MM_PARTS = MM_PARTS_D;             // worker warps per TMEM lane quadrant: each scans MM_N / MM_PARTS columns
-constexpr int MM_WWARPS = 4 * MM_PARTS;          // worker warps (warp MM_WWARPS issues the MMAs)
+constexpr int MM_WWARPS = 16;        // worker warps: TMEM quadrant w & 3, query half (w >> 2) & 1, column half w >> 3
 constexpr int MM_WORKERS = 32 * MM_WWARPS;
-constexpr int MM_THREADS = MM_WORKERS + 32;
-constexpr int MM_PCOLS = MM_N / MM_PARTS;        // columns per part: 64 (one packed TMEM load) or 128 (two)
-static_assert(MM_PARTS == 2 || MM_PARTS == 4, "2 or 4 column parts");
-constexpr int MM_A_BYTES = MM_M * 32 * MM_KB;   // 36,864
-constexpr int MM_B_BYTES = MM_N * 32 * MM_KB;   // 73,728
+constexpr int MM_THREADS = MM_WORKERS + 32;      // warp 16 issues the MMAs
+constexpr int MM_PARTS = 2;                      // column halves of a tile, scanned by different warps: key rows per split
+constexpr int MM_A_BYTES = MM_MQ * 32 * MM_KB;  // 73,728
+constexpr int MM_B_BYTES = MM_N * 32 * MM_KB;   // 36,864
 constexpr int MM_SMEM = 2 * MM_A_BYTES + 2 * MM_B_BYTES + 128;   // + barriers and the TMEM address
 constexpr int MM_IDX_BITS = 22;
 constexpr uint32_t MM_KEY_NONE = 0xffffffffu;
-constexpr int MM_BIAS = 16384;                  // acc + MM_BIAS = 128 d + (j mod 128)
+constexpr int MM_BIAS = 16384;                  // acc + MM_BIAS = 128 d + (train row inside its tile)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,7 +131,7 @@ __device__ __forceinline__ Item item_of(int it, int mtiles, int splits, int nt, 
   Item I;
   I.split = it % splits;
   const int r = it / splits;
-  I.q0 = (r % mtiles) * MM_M;
+  I.q0 = (r % mtiles) * MM_MQ;
   I.b = r / mtiles;
   I.t0 = I.split * per;
   I.t1 = min(nt, I.t0 + per);
@@ -159,8 +157,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
 hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt, int batch, int splits,
                    int per /* train rows per split, a multiple of MM_N */, uint2* __restrict__ keys /* [batch][MM_PARTS*splits][nq] */) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;                       // 2 query tiles
-  uint8_t* sB = smem + 2 * MM_A_BYTES;      // 2 train stages
+  uint8_t* sA = smem;                       // 2 query tiles of 256 rows
+  uint8_t* sB = smem + 2 * MM_A_BYTES;      // 2 train stages of 128 rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * MM_A_BYTES + 2 * MM_B_BYTES);  // full[2], done[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,16 +176,16 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // K block 8: a = (1, 0, ..., 0) for every query row, b = (j mod 128, 0, ..., 0) for train row j of a tile
-  for (int r = tid; r < 2 * MM_M; r += MM_THREADS) {
-    uint8_t* p = sA + (r / MM_M) * MM_A_BYTES + 8 * MM_M * 32 + row_off(r % MM_M);
+  // K block 8: a = (1, 0, ..., 0) for every query row, b = (j, 0, ..., 0) for train row j of a tile
+  for (int r = tid; r < 2 * MM_MQ; r += MM_THREADS) {
+    uint8_t* p = sA + (r / MM_MQ) * MM_A_BYTES + 8 * MM_MQ * 32 + row_off(r % MM_MQ);
     *reinterpret_cast<uint4*>(p) = make_uint4(1u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
   }
   for (int r = tid; r < 2 * MM_N; r += MM_THREADS) {
     const int j = r % MM_N;
     uint8_t* p = sB + (r / MM_N) * MM_B_BYTES + 8 * MM_N * 32 + row_off(j);
-    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)(j & 127), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)j, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_async_smem();
@@ -196,11 +194,11 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int mtiles = (nq + MM_M - 1) / MM_M;
+  const int mtiles = (nq + MM_MQ - 1) / MM_MQ;
   const int nitems = batch * mtiles * splits;
 
   if (warp == MM_WWARPS) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: per tile 2 x 9 MMAs (query rows 0-127 and 128-255) into the stage's two accumulators =====
     uint32_t g = 0;
     int seq = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++seq) {
@@ -213,19 +211,20 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
         if (lane == 0) {
           const uint32_t b_addr = smem_u32(sB + s * MM_B_BYTES);
 #pragma unroll
-          for (int kb = 0; kb < MM_KB; ++kb)
-            mma_i8(tmem_base + s * MM_N, smem_desc(a_addr + kb * MM_M * 32, 128, 256), smem_desc(b_addr + kb * MM_N * 32, 128, 256),
-                   kb > 0 ? 1u : 0u);
-          mma_commit(bar_done + 8 * s);  // arrives when the nine MMAs have read their operands and written the accumulator
+          for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+            for (int kb = 0; kb < MM_KB; ++kb)
+              mma_i8(tmem_base + (2 * s + mh) * MM_N, smem_desc(a_addr + kb * MM_MQ * 32 + mh * MM_M * 32, 128, 256),
+                     smem_desc(b_addr + kb * MM_N * 32, 128, 256), kb > 0 ? 1u : 0u);
+          mma_commit(bar_done + 8 * s);  // arrives when the MMAs have read their operands and written the accumulators
         }
         __syncwarp();
       }
     }
   } else {
     // ===== workers: unpack tile g, scan tile g-1 =====
-    const uint4* t4 = reinterpret_cast<const uint4*>(t);
-    const int quad = warp & 3, part = warp >> 2;
-    const int row = quad * 32 + lane;                       // the query row (TMEM lane) this thread scans
+    const int quad = warp & 3, mh = (warp >> 2) & 1, part = warp >> 3;
+    const int row = mh * MM_M + quad * 32 + lane;           // the query row of the item this thread scans
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t g = 0;
     int seq = 0;
@@ -233,25 +232,19 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     int p_valid = 0, p_tbase = 0, p_b = 0, p_q0 = 0, p_split = 0;
     bool p_first = false, p_last = false, have_prev = false;
     uint32_t K1 = MM_KEY_NONE, K2 = MM_KEY_NONE;
-    uint4 nw0 = make_uint4(0u, 0u, 0u, 0u), nw1 = nw0;  // this thread's words of the next train tile
-    bool have_next = false;
+    // this thread's words of the next train tile (row tid & 127, words 2 (tid >> 7) ..) and of the next query tile
+    // (row tid & 255, words 4 (tid >> 8) ..), requested one tile / one item ahead
+    uint2 nw = make_uint2(0u, 0u);
+    uint4 qw = make_uint4(0u, 0u, 0u, 0u);
+    bool have_next = false, have_q = false;
     auto load_train = [&](int b, int t0) {
-      constexpr int WPT = 8 * MM_N / MM_WORKERS;
-      const int r = tid & (MM_N - 1), hw = tid >> 8;
-      const uint4* src = t4 + ((size_t)b * nt + min(t0 + r, nt - 1)) * 2 + (WPT == 4 ? hw : 0);
-      nw0 = __ldg(src);
-      if (WPT == 8) nw1 = __ldg(src + 1);
+      const int r = tid & (MM_N - 1), pr = tid >> 7;
+      nw = __ldg(reinterpret_cast<const uint2*>(t + ((size_t)b * nt + min(t0 + r, nt - 1)) * 8) + pr);
       have_next = true;
     };
-
-    uint4 qw = make_uint4(0u, 0u, 0u, 0u);  // this thread's words of the next query tile
-    bool have_q = false;
     auto load_query = [&](int b, int q0) {
-      constexpr int WPT = 8 * MM_M / MM_WORKERS;
-      const int r = tid & (MM_M - 1), hw = tid >> 7;
-      const uint32_t* src = q + ((size_t)b * nq + min(q0 + r, nq - 1)) * 8 + WPT * hw;
-      if (WPT == 4) qw = __ldg(reinterpret_cast<const uint4*>(src));
-      else { const uint2 x = __ldg(reinterpret_cast<const uint2*>(src)); qw.x = x.x; qw.y = x.y; }
+      const int r = tid & (MM_MQ - 1), hw = tid >> 8;
+      qw = __ldg(reinterpret_cast<const uint4*>(q + ((size_t)b * nq + min(q0 + r, nq - 1)) * 8) + hw);
       have_q = true;
     };
 
@@ -260,16 +253,12 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
       mbar_wait(bar_done + 8 * s, ((g - 1) >> 1) & 1);
       tc_fence_after();
       if (p_first) K1 = K2 = MM_KEY_NONE;
-      // this warp's MM_PCOLS columns, 64 per packed load; 0x7fff = no candidate in that half-register
+      // this warp's 64 columns in one packed load; 0x7fff = no candidate in that half-register
       uint32_t k1 = 0x7fff7fffu, k2 = 0x7fff7fffu;
-      const int col_base = part * MM_PCOLS;
-      const uint32_t tcol = tmem_base + lane_addr + s * MM_N + col_base;
-#pragma unroll 1
-      for (int c = 0; c < MM_PCOLS / 64; ++c) {
-        const int col0 = col_base + c * 64;
-        if (col0 >= p_valid) break;  // warp-uniform
+      const int col0 = part * 64;
+      if (col0 < p_valid) {  // warp-uniform
         uint32_t v[32];
-        tmem_ld64_packed(tcol + c * 64, v);
+        tmem_ld64_packed(tmem_base + lane_addr + (2 * s + mh) * MM_N + col0, v);
         tmem_ld_wait();
         if (col0 + 64 > p_valid) {  // the last tile of a train range: columns >= p_valid hold stale rows
 #pragma unroll
@@ -287,11 +276,11 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
         const int m1 = min(a1, b1), m2 = min(max(a1, b1), min(a2, b2));
         if (m1 != 0x7fff) {
           const uint32_t u = (uint32_t)(m1 + MM_BIAS);
-          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (col_base & 128) + (int)(u & 127u)), K1, K2);
+          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (int)(u & 127u)), K1, K2);
         }
         if (m2 != 0x7fff) {
           const uint32_t u = (uint32_t)(m2 + MM_BIAS);
-          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (col_base & 128) + (int)(u & 127u)), K1, K2);
+          top2_u(((u >> 7) << MM_IDX_BITS) | (uint32_t)(p_tbase + (int)(u & 127u)), K1, K2);
         }
       }
       if (p_last && p_q0 + row < nq)
@@ -304,31 +293,27 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
       for (int t0 = I.t0; t0 < I.t1; t0 += MM_N, ++g) {
         const uint32_t s = g & 1;
         if (t0 == I.t0) {
-          // query tile of this item: 128 rows x 8 words over the worker threads (requested with the previous item's
-          // last train tile, except for this CTA's first item)
-          constexpr int WPT = 8 * MM_M / MM_WORKERS;  // words per thread: 4 (256 workers) or 2 (512)
-          const int r = tid & (MM_M - 1), hw = tid >> 7;
+          // query tile of this item: 256 rows x 8 words, four words per thread
+          const int r = tid & (MM_MQ - 1), hw = tid >> 8;
           if (!have_q) load_query(I.b, I.q0);
           have_q = false;
           uint8_t* base = sA + (seq & 1) * MM_A_BYTES + row_off(r);
           const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
-          for (int i = 0; i < WPT; ++i) unpack_word<XOR_A>(w[i], base + (WPT * hw + i) * MM_M * 32);
+          for (int i = 0; i < 4; ++i) unpack_word<XOR_A>(w[i], base + (4 * hw + i) * MM_MQ * 32);
         }
         {
-          // train tile: 256 rows x 8 words over the worker threads; the words were requested one tile ago (the L2 round
-          // trip of these loads was the kernel's top stall when they were issued here)
-          constexpr int WPT = 8 * MM_N / MM_WORKERS;  // 8 or 4
-          const int r = tid & (MM_N - 1), hw = tid >> 8;
+          // train tile: 128 rows x 8 words, two words per thread (requested one tile ago: the L2 round trip of these
+          // loads was the kernel's top stall when they were issued here)
+          const int r = tid & (MM_N - 1), pr = tid >> 7;
           if (!have_next) load_train(I.b, t0);
           uint8_t* base = sB + s * MM_B_BYTES + row_off(r);
-          uint32_t w[8] = {nw0.x, nw0.y, nw0.z, nw0.w, nw1.x, nw1.y, nw1.z, nw1.w};
-#pragma unroll
-          for (int i = 0; i < WPT; ++i) unpack_word<XOR_B>(w[i], base + ((WPT == 4 ? 4 * hw : 0) + i) * MM_N * 32);
+          unpack_word<XOR_B>(nw.x, base + (2 * pr + 0) * MM_N * 32);
+          unpack_word<XOR_B>(nw.y, base + (2 * pr + 1) * MM_N * 32);
         }
         fence_async_smem();              // generic-proxy stores -> visible to the tensor core's async proxy
         mbar_arrive(bar_full + 8 * s);
-        // request the next tile's rows (of this item, or the first tile of this CTA's next item) before the scan
+        // request the next tile's rows (of this item, or the first tile and the queries of this CTA's next item)
         have_next = false;
         if (t0 + MM_N < I.t1) {
           load_train(I.b, t0 + MM_N);
@@ -370,7 +355,7 @@ int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int
     if (e != cudaSuccess) return -(int)e;
     configured = true;
   }
-  const int mtiles = (nq + MM_M - 1) / MM_M;
+  const int mtiles = (nq + MM_MQ - 1) / MM_MQ;
   const int ntiles = (nt + MM_N - 1) / MM_N;
   // split the train set over CTAs when the query tiles alone cannot fill the GPU
   int splits = 1;
