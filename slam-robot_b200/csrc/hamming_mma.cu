@@ -230,7 +230,7 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
     int seq = 0;
     // state of the tile whose accumulators are scanned next (tile g-1)
     int p_valid = 0, p_tbase = 0, p_b = 0, p_q0 = 0, p_split = 0;
-    bool p_first = false, p_last = false, have_prev = false;
+    bool p_first = false, p_last = false, p_long = false, have_prev = false;
     uint32_t K1 = MM_KEY_NONE, K2 = MM_KEY_NONE;
     // this thread's words of the next train tile (row tid & 127, words 2 (tid >> 7) ..) and of the next query tile
     // (row tid & 255, words 4 (tid >> 8) ..), requested one tile / one item ahead
@@ -267,8 +267,24 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
             v[r] = cc + 1 < p_valid ? v[r] : (cc < p_valid ? (v[r] | 0x7fff0000u) & 0x7fffffffu : 0x7fff7fffu);
           }
         }
+        // Against a long train range almost no tile holds a column that can still enter a query's two best: one pass of
+        // three-input minima finds the tile's smallest key, and the scan proper runs only if some lane of the warp needs
+        // it (a tie in distance counts as needed, so the lowest-index rule is untouched).  With a few thousand train rows
+        // some lane of the 32 almost always does, so there the test would be pure overhead and is left out.
+        bool scan = true;
+        if (p_long) {
+          uint32_t mm = v[0];
 #pragma unroll
-        for (int r = 0; r < 32; r += 2) top2_pair_s16x2(v[r], v[r + 1], k1, k2);
+          for (int r = 1; r + 1 < 32; r += 2) mm = __vimin3_s16x2(mm, v[r], v[r + 1]);
+          mm = __vmins2(mm, v[31]);
+          const int cmin = min((int)(short)(mm & 0xffffu), (int)mm >> 16);
+          const int reach = (int)((K2 >> MM_IDX_BITS) << 7) + 127 - MM_BIAS;  // largest key a column of this thread's second-best distance can have
+          scan = __any_sync(0xffffffffu, cmin <= reach);
+        }
+        if (scan) {
+#pragma unroll
+          for (int r = 0; r < 32; r += 2) top2_pair_s16x2(v[r], v[r + 1], k1, k2);
+        }
       }
       // even and odd columns each kept their own two smallest: the tile's two winners are the two smallest of those four
       {
@@ -328,6 +344,7 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
         p_b = I.b; p_q0 = I.q0; p_split = I.split;
         p_first = t0 == I.t0;
         p_last = t0 + MM_N >= I.t1;
+        p_long = I.t1 - I.t0 >= 16384;
         have_prev = true;
       }
     }

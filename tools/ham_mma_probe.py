@@ -48,7 +48,7 @@ def timeit(nq, nt, batch, impl, reps=5):
     print("nq %d nt %d batch %d impl %d: %.3f ms  %.1f G comparisons/s" % (nq, nt, batch, impl, ms, nq * nt * batch / ms / 1e6), flush=True)
     return out
 
-for shape in [(2000, 2000, 512), (65536, 65536, 1), (500, 500, 1)]:
+for shape in [(2000, 2000, 512), (65536, 65536, 1), (262144, 262144, 1), (500, 500, 1)]:
     a = timeit(*shape, 1)
     b = timeit(*shape, 2)
     print("   identical:", all(bool((x == y).all()) for x, y in zip(a, b)))
