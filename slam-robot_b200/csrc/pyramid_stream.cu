@@ -308,7 +308,7 @@ struct RowBufs {
   float2 pd[NL + 2];                       // pyrDown row: pd[L+1]; written in even ticks, read in odd ticks
 };
 
-template <int NW, int BLUR0, int BLUR1>
+template <int NW, int BLUR0, int BLUR1, bool BULK = false>
 #ifndef ROW_MINB5
 #define ROW_MINB5 4  // measured: 4 CTAs x 5 warps at 94 registers beat 5 CTAs at 72 (profiles/README.md)
 #endif
@@ -318,7 +318,19 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, L = threadIdx.x;
   const int band = blockIdx.x % a.bands;
   const int frame = blockIdx.x / a.bands;
-  unsigned char* ring = row_smem + sizeof(Bufs) + (size_t)warp * RING * 32 * 12;
+  // BULK: a CTA owns whole rows, and a row's BGR bytes are one contiguous, 16-byte aligned run of 384 NW bytes -- one
+  // cp.async.bulk transaction through the TMA unit per row (issued by thread 0, completed on the slot's mbarrier) instead
+  // of three 4-byte cp.async per lane; the ring is then [slot][row bytes] and lane L reads bytes 12 L ...
+  unsigned char* ring = BULK ? row_smem + sizeof(Bufs) : row_smem + sizeof(Bufs) + (size_t)warp * RING * 32 * 12;
+  __shared__ __align__(8) unsigned long long ring_bar[RING];
+  constexpr uint32_t ROW_BYTES = 384 * NW;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(ring_bar);
+  if (BULK && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < RING; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (BULK) __syncthreads();
 
   const int g = 4 * L;
   // OpenCV's scalar-path columns of the horizontal pyrDown pass (pyr_math.cuh): column 0 and the last few, i.e. lanes
@@ -354,8 +366,24 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   const int t_begin = r0 - 8;   // even: qd is even exactly when the unrolled tick index is
   const int t_last = r1 + 9;
   const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring + lane * 12);
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint8_t* frame_px = a.bgr + (size_t)frame * a.frame_stride;
+  auto bulk_row = [&](int slot, int t) {   // thread 0 only
+    const uint8_t* src = frame_px + (size_t)reflect_row(t, a.h) * a.row_stride;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * slot), "r"(ROW_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ring_base + slot * ROW_BYTES), "l"(src), "r"(ROW_BYTES), "r"(bar0 + 8 * slot) : "memory");
+  };
+  if (BULK) {
+    if (threadIdx.x == 0)
+      for (int u = 0; u < PREFETCH; ++u) bulk_row(u, t_begin + u);
+  } else {
 #pragma unroll
-  for (int u = 0; u < PREFETCH; ++u) issue_row<true>(ring_addr + u * 32 * 12, a, bgr_px, nullptr, t_begin + u, 4);
+    for (int u = 0; u < PREFETCH; ++u) issue_row<true>(ring_addr + u * 32 * 12, a, bgr_px, nullptr, t_begin + u, 4);
+  }
+  uint32_t round = 0;   // how often the ring has wrapped: the parity the slot barriers are waited with
+  const int t_exec_last = t_begin + 10 * ((t_last - t_begin) / 10 + 1) - 1;   // the loop runs whole blocks of ten ticks
 
   float4 hbw[5];   // horizontally blurred gray rows t-5..t-1
   float2 phw[5];   // horizontally pyrDown-filtered rows qd-4..qd
@@ -376,11 +404,21 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
       const int t = tb + u;
       const uint32_t cur = (u & 1) * BUF, prev = ((u + 1) & 1) * BUF;
       __syncthreads();
-      asm volatile("cp.async.wait_group %0;" ::"n"(PREFETCH - 1) : "memory");
-      issue_row<true>(ring_addr + ((u + PREFETCH) % RING) * 32 * 12, a, bgr_px, nullptr, t + PREFETCH, 4);
+      const uint32_t* rr;
+      if (BULK) {
+        if (threadIdx.x == 0 && t + PREFETCH <= t_exec_last) bulk_row((u + PREFETCH) % RING, t + PREFETCH);   // the slot read two ticks ago
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bar0 + 8 * (u % RING)), "r"(round & 1u) : "memory");
+        rr = reinterpret_cast<const uint32_t*>(ring + (u % RING) * ROW_BYTES + 12 * L);
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(PREFETCH - 1) : "memory");
+        issue_row<true>(ring_addr + ((u + PREFETCH) % RING) * 32 * 12, a, bgr_px, nullptr, t + PREFETCH, 4);
+        rr = reinterpret_cast<const uint32_t*>(ring + ((u % RING) * 32 + lane) * 12);
+      }
 
       // ---- gray(t), published for the next tick
-      const uint32_t* rr = reinterpret_cast<const uint32_t*>(ring + ((u % RING) * 32 + lane) * 12);
       const float4 gn = gray4(rr[0], rr[1], rr[2]);
       sts2(lb + GXY + cur, gn.x, gn.y);
       sts2(lb + GZW + cur + 8, gn.z, gn.w);
@@ -446,6 +484,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
       gp = gn;
       rowp = row;
     }
+    ++round;
   }
 }
 
@@ -491,15 +530,15 @@ size_t row_smem_bytes() { return sizeof(RowBufs<NW>) + (size_t)NW * RING * 32 * 
 // time, so what matters is how the grid quantises into waves: measured on B200 (128..1024 VGA frames, 1..8 bands,
 // profiles/README.md) the best grids hold about 1.73x the resident CTA slots -- one full wave plus a second one
 // that finishes quickly because its CTAs have the SMs almost to themselves -- or 0.86x when that is all there is.
-template <int NW>
-void launch_row(StreamArgs& a, int count, cudaStream_t s) {
+template <int NW, bool BULK>
+void launch_row_impl(StreamArgs& a, int count, cudaStream_t s) {
   static int slots = 0;  // resident CTAs on the device
   if (slots == 0) {
     int dev = 0, per_sm = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1>, 32 * NW, row_smem_bytes<NW>());
+    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1, BULK>, 32 * NW, row_smem_bytes<NW>());
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int rows = 2 * a.h1;
@@ -516,7 +555,16 @@ void launch_row(StreamArgs& a, int count, cudaStream_t s) {
   a.bands = (rows + br - 1) / br;
   a.strips = 1;
   a.nunits = count * a.bands;
-  pyr_row_kernel<NW, 0, 1><<<a.nunits, 32 * NW, row_smem_bytes<NW>(), s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+  pyr_row_kernel<NW, 0, 1, BULK><<<a.nunits, 32 * NW, row_smem_bytes<NW>(), s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+}
+template <int NW>
+void launch_row(StreamArgs& a, int count, cudaStream_t s) {
+  // rows through cp.async.bulk (the TMA unit) when every row starts 16-byte aligned: measured 0.628 -> 0.600 ms per 1024
+  // VGA frames against three 4-byte cp.async per lane (profiles/README.md); SFE_PYR_BULK=0 switches it off (experiments)
+  static const bool want_bulk = !(getenv("SFE_PYR_BULK") && atoi(getenv("SFE_PYR_BULK")) == 0);
+  const bool aligned = (((uintptr_t)a.bgr | a.row_stride | a.frame_stride) & 15) == 0;
+  if (want_bulk && aligned) launch_row_impl<NW, true>(a, count, s);
+  else launch_row_impl<NW, false>(a, count, s);
 }
 
 }  // namespace
