@@ -308,7 +308,7 @@ struct RowBufs {
   float2 pd[NL + 2];                       // pyrDown row: pd[L+1]; written in even ticks, read in odd ticks
 };
 
-template <int NW, int BLUR0, int BLUR1, bool BULK = false>
+template <int NW, int BLUR0, int BLUR1, bool BULK = false, int SEGS = 1>
 #ifndef ROW_MINB5
 #define ROW_MINB5 4  // measured: 4 CTAs x 5 warps at 94 registers beat 5 CTAs at 72 (profiles/README.md)
 #endif
@@ -316,8 +316,20 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   using Bufs = RowBufs<NW>;
   extern __shared__ __align__(16) unsigned char row_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, L = threadIdx.x;
-  const int band = blockIdx.x % a.bands;
-  const int frame = blockIdx.x / a.bands;
+  // SEGS > 1 (frames wider than one CTA can hold at a useful residency, e.g. 1920 columns as two 8-warp CTAs): the row is
+  // cut into SEGS column segments of w / SEGS useful columns; a CTA's 128 NW lane-columns start at x0 (a multiple of 16, so
+  // a segment's BGR bytes stay 16-byte aligned) and the lanes outside [lane_lo, lane_hi) are halo -- they recompute the
+  // neighbour's columns (>= 8 are needed for blur o pyrDown o blur) and store nothing.  The row-buffer slots beyond a cut
+  // edge are never written; what is read from them only reaches halo lanes.
+  const int seg = SEGS > 1 ? blockIdx.x % SEGS : 0;
+  const int unit = SEGS > 1 ? blockIdx.x / SEGS : blockIdx.x;
+  const int band = unit % a.bands;
+  const int frame = unit / a.bands;
+  const int seg_w = a.w / SEGS;
+  const int x0 = SEGS == 1 || seg == 0 ? 0 : (seg == SEGS - 1 ? a.w - 128 * NW : (seg * seg_w - (128 * NW - seg_w) / 2) & ~15);
+  const int lane_lo = (seg * seg_w - x0) >> 2;
+  const bool useful = SEGS == 1 || (L >= lane_lo && L < lane_lo + (seg_w >> 2));
+  const bool edge_l = SEGS == 1 || seg == 0, edge_r = SEGS == 1 || seg == SEGS - 1;
   // BULK: a CTA owns whole rows, and a row's BGR bytes are one contiguous, 16-byte aligned run of 384 NW bytes -- one
   // cp.async.bulk transaction through the TMA unit per row (issued by thread 0, completed on the slot's mbarrier) instead
   // of three 4-byte cp.async per lane; the ring is then [slot][row bytes] and lane L reads bytes 12 L ...
@@ -332,10 +344,10 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   }
   if (BULK) __syncthreads();
 
-  const int g = 4 * L;
+  const int g = x0 + 4 * L;
   // OpenCV's scalar-path columns of the horizontal pyrDown pass (pyr_math.cuh): column 0 and the last few, i.e. lanes
   // of the first and the last warp only (w1 = 64 NW is a multiple of 8: the level-1 column blur has no tail)
-  const bool tail_x = pd_h_tail(2 * L, a.hbody), tail_y = pd_h_tail(2 * L + 1, a.hbody);
+  const bool tail_x = pd_h_tail(g >> 1, a.hbody), tail_y = pd_h_tail((g >> 1) + 1, a.hbody);
   const bool warp_tail = __any_sync(SFE_FULL, tail_x || tail_y);
   const int r0 = band * a.band_rows;
   const int r1 = min(r0 + a.band_rows, 2 * a.h1);
@@ -352,11 +364,11 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
                      PD = offsetof(Bufs, pd), BUF = 8 * (Bufs::NL + 1);
   // image borders: the first lane of the row also fills zw slot 0 (columns -2, -1 = 2, 1), the last lane xy slot NL
   // (columns w, w+1 = w-2, w-3); both are (z, y) of the lane.  `mb` is that slot relative to GXY + buffer offset.
-  const int mirror = L == 0 || L == Bufs::NL - 1;
+  const int mirror = (L == 0 && edge_l) || (L == Bufs::NL - 1 && edge_r);
   const uint32_t mb = L == 0 ? lb + (GZW - GXY) : lb + 8;
   // pyrDown row: slot 0 = columns (2, 1) = (pa of lane 1, pb of lane 0); slot NL+1 = columns (w1-2, w1-3) =
   // (pa of the last lane, pb of the one before): odd lanes store their pa into .x, even lanes their pb into .y
-  const int pd_mirror = L < 2 || L >= Bufs::NL - 2;
+  const int pd_mirror = (L < 2 && edge_l) || (L >= Bufs::NL - 2 && edge_r);
   const uint32_t pmb = (L < 2 ? lb - 8 * L : lb + 8 * (Bufs::NL + 1 - L)) + PD + ((L & 1) ? 0 : 4);
 
   // Tick t: BGR row t arrives and becomes gray(t); the lagged stages then work on
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
   const uint8_t* frame_px = a.bgr + (size_t)frame * a.frame_stride;
   auto bulk_row = [&](int slot, int t) {   // thread 0 only
-    const uint8_t* src = frame_px + (size_t)reflect_row(t, a.h) * a.row_stride;
+    const uint8_t* src = frame_px + (size_t)reflect_row(t, a.h) * a.row_stride + 3 * (size_t)x0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * slot), "r"(ROW_BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -443,7 +455,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
       const float2 rzw = blur_col2(make_float2(h0.z, h0.w), make_float2(h1.z, h1.w), make_float2(h2.z, h2.w),
                                    make_float2(h3.z, h3.w), make_float2(h4.z, h4.w), k0);
       const float4 row = make_float4(rxy.x, rxy.y, rzw.x, rzw.y);
-      if (q >= r0 && q < q_hi) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
+      if (q >= r0 && q < q_hi && useful) *reinterpret_cast<float4*>(out0_px + (size_t)q * a.out0_pitch) = row;
       sts2(lb + LXY + cur, row.x, row.y);
       sts2(lb + LZW + cur + 8, row.z, row.w);
       sts1_if(mirror, mb + LXY + cur, row.z);
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 5 ? ROW_MINB5 : (NW <= 10 ? 2 :
         bhw[v] = bh;
         const float2 &b0 = bhw[(v + 1) % 5], &b1 = bhw[(v + 2) % 5], &b2 = bhw[(v + 3) % 5], &b3 = bhw[(v + 4) % 5], &b4 = bhw[v];
         const int j = i - 2;
-        if (j >= j_lo && j < j_hi)
+        if (j >= j_lo && j < j_hi && useful)
           *reinterpret_cast<float2*>(out1_px + (size_t)j * a.out1_pitch) = blur_col2(b0, b1, b2, b3, b4, k1);
       }
       gp = gn;
@@ -513,7 +525,8 @@ void plan_bands(StreamArgs& a, int count) {
   int bands = (int)(1.3 * slots / ((double)count * a.strips) + 0.5);
   static const int forced = getenv("SFE_PYR_BANDS") ? atoi(getenv("SFE_PYR_BANDS")) : 0;  // experiments
   if (forced > 0) bands = forced;
-  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
+  static const int min_band = getenv("SFE_PYR_MIN_BAND") ? atoi(getenv("SFE_PYR_MIN_BAND")) : 40;  // experiments
+  const int max_bands = rows / min_band > 0 ? rows / min_band : 1;
   if (bands < 1) bands = 1;
   if (bands > max_bands) bands = max_bands;
   int br = (rows + bands - 1) / bands;
@@ -526,45 +539,64 @@ void plan_bands(StreamArgs& a, int count) {
 template <int NW>
 size_t row_smem_bytes() { return sizeof(RowBufs<NW>) + (size_t)NW * RING * 32 * 12; }
 
-// Bands of the row-CTA kernel: a CTA is NW warps, a band repeats 18 rows of pipeline fill.  All CTAs take the same
-// time, so what matters is how the grid quantises into waves: measured on B200 (128..1024 VGA frames, 1..8 bands,
-// profiles/README.md) the best grids hold about 1.73x the resident CTA slots -- one full wave plus a second one
-// that finishes quickly because its CTAs have the SMs almost to themselves -- or 0.86x when that is all there is.
-template <int NW, bool BULK>
+// Bands of the row-CTA kernel: a CTA is NW warps, a band repeats 18 rows of pipeline fill (which store nothing: about 7
+// rows' worth of time in this write-bound kernel).  All CTAs take the same time, so what matters is how the grid
+// quantises into waves.  Fitted to measurements on B200 (128..1024 VGA frames, 64..128 frames of 1920 x 1080, 1..12
+// bands, profiles/README.md), in units of one CTA time: a grid below one wave costs 0.45 + 0.55 of its fill (fewer CTAs
+// per SM hide less latency), full waves cost 1 each, a partial last wave its fraction but at least 0.5 (its CTAs have
+// the SMs almost to themselves).  The band count minimises that cost times (band rows + 7): the grids that win hold
+// about 1.73 or 2.77 waves, the ones just above a whole number of waves lose up to 15 %.
+static int pick_bands(int ctas_per_band, int slots, int rows, int max_bands) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int b = 1; b <= max_bands; ++b) {
+    int br = (rows + b - 1) / b;
+    br += br & 1;
+    const int nb = (rows + br - 1) / br;
+    const double w = (double)ctas_per_band * nb / slots;
+    const double full = (double)(long long)w, frac = w - full;
+    const double waves = w < 1. ? 0.45 + 0.55 * w : full + (frac > 0. ? (frac > 0.5 ? frac : 0.5) : 0.);
+    const double cost = waves * (br + 7);
+    if (cost < best_cost * 0.999) best_cost = cost, best = b;
+  }
+  return best;
+}
+
+template <int NW, bool BULK, int SEGS>
 void launch_row_impl(StreamArgs& a, int count, cudaStream_t s) {
   static int slots = 0;  // resident CTAs on the device
   if (slots == 0) {
     int dev = 0, per_sm = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1, BULK>, 32 * NW, row_smem_bytes<NW>());
+    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1, BULK, SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1, BULK, SEGS>, 32 * NW, row_smem_bytes<NW>());
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int rows = 2 * a.h1;
-  static const double fill = getenv("SFE_PYR_ROW_FILL") ? atof(getenv("SFE_PYR_ROW_FILL")) : 1.73;  // experiments
-  int bands = (int)(fill * slots / (double)count + 0.5);
+  static const double fill = getenv("SFE_PYR_ROW_FILL") ? atof(getenv("SFE_PYR_ROW_FILL")) : 0.;  // experiments: ctas = fill * slots
+  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
+  int bands = fill > 0. ? (int)(fill * slots / ((double)count * SEGS) + 0.5) : pick_bands(count * SEGS, slots, rows, max_bands);
   static const int forced = getenv("SFE_PYR_BANDS") ? atoi(getenv("SFE_PYR_BANDS")) : 0;
   if (forced > 0) bands = forced;
-  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
   if (bands < 1) bands = 1;
   if (bands > max_bands) bands = max_bands;
   int br = (rows + bands - 1) / bands;
   br += br & 1;
   a.band_rows = br;
   a.bands = (rows + br - 1) / br;
-  a.strips = 1;
-  a.nunits = count * a.bands;
-  pyr_row_kernel<NW, 0, 1, BULK><<<a.nunits, 32 * NW, row_smem_bytes<NW>(), s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
+  a.strips = SEGS;
+  a.nunits = count * a.bands * SEGS;
+  pyr_row_kernel<NW, 0, 1, BULK, SEGS><<<a.nunits, 32 * NW, row_smem_bytes<NW>(), s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)
 }
-template <int NW>
+template <int NW, int SEGS = 1>
 void launch_row(StreamArgs& a, int count, cudaStream_t s) {
   // rows through cp.async.bulk (the TMA unit) when every row starts 16-byte aligned: measured 0.628 -> 0.600 ms per 1024
   // VGA frames against three 4-byte cp.async per lane (profiles/README.md); SFE_PYR_BULK=0 switches it off (experiments)
   static const bool want_bulk = !(getenv("SFE_PYR_BULK") && atoi(getenv("SFE_PYR_BULK")) == 0);
   const bool aligned = (((uintptr_t)a.bgr | a.row_stride | a.frame_stride) & 15) == 0;
-  if (want_bulk && aligned) launch_row_impl<NW, true>(a, count, s);
-  else launch_row_impl<NW, false>(a, count, s);
+  if (want_bulk && aligned) launch_row_impl<NW, true, SEGS>(a, count, s);
+  else launch_row_impl<NW, false, SEGS>(a, count, s);
 }
 
 }  // namespace
@@ -596,9 +628,15 @@ int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_s
       a.bgr = bgr; a.row_stride = row_stride; a.frame_stride = frame_stride;
       a.out0 = v.base[0][0]; a.out0_fs = v.frame_stride[0]; a.out0_pitch = v.pitch[0];
       static const bool strips_only = getenv("SFE_PYR_STRIPS") != nullptr;  // experiments: force the strip kernel
+      static const bool no_segs = getenv("SFE_PYR_NOSEG") != nullptr;        // experiments: 1920 columns on the strip kernel
+      static const bool segs2 = getenv("SFE_PYR_SEG") && atoi(getenv("SFE_PYR_SEG")) == 2;    // experiments
       // row-CTA kernel for the widths it was tuned for; 1920 columns would be one 15-warp CTA per SM (slower than strips)
       if (!strips_only && a.w == 640) launch_row<5>(a, count, s);
       else if (!strips_only && a.w == 1280) launch_row<10>(a, count, s);
+      // 1920 columns: one 15-warp CTA per SM loses to the strips, so the row is cut into column segments with halo lanes --
+      // four 4-warp CTAs of 480 useful columns (5 CTAs = 20 warps per SM, as at 640 columns); two 8-warp CTAs are slower
+      else if (!strips_only && !no_segs && a.w == 1920 && segs2) launch_row<8, 2>(a, count, s);
+      else if (!strips_only && !no_segs && a.w == 1920) launch_row<4, 4>(a, count, s);
       else {
         plan_bands<true>(a, count);
         pyr_stream_kernel<true, 0, 1><<<a.nunits, 32, 0, s>>>(a);  // sigma 1.1 then 0.8 (hessian.h:102,113)

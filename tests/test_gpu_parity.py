@@ -44,7 +44,7 @@ def test_pyramid_1080p_8_levels_bit_exact(fe, po, synth):
 
 
 @pytest.mark.parametrize("shape,depth,nframes", [((480, 640), 4, 3), ((481, 640), 5, 2), ((97, 640), 3, 2), ((720, 1280), 6, 2),
-                                                 ((45, 1280), 2, 1), ((1080, 1920), 4, 1), ((16, 640), 2, 2), ((17, 640), 2, 1), ((18, 640), 3, 1)])
+                                                 ((45, 1280), 2, 1), ((1080, 1920), 4, 1), ((541, 1920), 3, 2), ((16, 640), 2, 2), ((17, 640), 2, 1), ((18, 640), 3, 1)])
 def test_pyramid_row_kernel_bit_exact(fe, po, synth, shape, depth, nframes):
     """Widths of 640 / 1280 / 1920 columns take the row-CTA kernel (pyramid_stream.cu: one CTA per row band, neighbours
     through shared row buffers, lagged stages): odd heights, bands shorter than the pipeline fill, several bands."""
