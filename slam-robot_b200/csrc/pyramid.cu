@@ -198,7 +198,10 @@ int build_chunk(const PyrView& v, int flavor, const uint8_t* bgr, size_t row_str
   if (built > 0) {
     --launches;  // level 0 came with the streaming kernel (the increment below counts this branch's launch)
   } else if (flavor == SFE_HESSIAN) pyr_l0_kernel<SFE_HESSIAN><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
-  else if (flavor == SFE_KLT) pyr_l0_kernel<SFE_KLT><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
+  else if (flavor == SFE_KLT) {
+    if (!launch_pyr_stream_klt_l0(v, bgr, row_stride, frame_stride, first, count, s))
+      pyr_l0_kernel<SFE_KLT><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
+  }
   else pyr_l0_kernel<SFE_BRUTE><<<g0, L0_THREADS, 0, s>>>(v, bgr, row_stride, frame_stride, first);
   ++launches;
   for (int l = built > 0 ? built : 1; l < v.depth; ++l) {

@@ -49,6 +49,7 @@ struct StreamArgs {
   int strips, bands, band_rows, nunits;
   float scale;             // DOWN_ONLY: factor applied to the pyrDown result (klt.h:123-124 doubles the gradients)
   int hbody;               // pd_hbody(w): last output column of cv::pyrDown's horizontal vector body
+  float *out_gx, *out_gy;  // klt_l0_stream_kernel: the Scharr planes of level 0 (frame stride / pitch of out0)
 };
 
 __device__ __forceinline__ float gray_px(uint32_t p) {
@@ -273,6 +274,72 @@ __device__ __forceinline__ float4 gray4(uint32_t ra, uint32_t rb, uint32_t rc) {
   g.z = gray_from_dot(__dp2a_lo(C2, rc, __dp2a_hi(C0 | (C1 << 16), rb, RND)));          // rb.b2 rb.b3 rc.b0
   g.w = gray_from_dot(__dp2a_hi(C1 | (C2 << 16), rc, __dp2a_lo(C0 << 16, rc, RND)));    // rc.b1 rc.b2 rc.b3
   return g;
+}
+
+// Level 0 of the klt.h flavour (klt.h:98-106): the gray plane as it is and its Scharr/32 gradient pair, streamed like the
+// strips above -- one warp per (frame, row band, 128-column strip), every lane four columns, walking down the rows with the
+// last three rows of the two separable row passes in registers.  The 3x3 filters reach one column, so one halo lane on
+// each side (120 useful columns per strip) and one row above / below the band suffice.  Arithmetic and operation order are
+// pyr_l0_kernel<SFE_KLT>'s (pyramid.cu), i.e. the oracle's orc_scharr for even widths.
+constexpr int KLT_USEFUL = 120;
+__global__ void __launch_bounds__(32) klt_l0_stream_kernel(const StreamArgs a) {
+  const int lane = threadIdx.x;
+  const int unit = blockIdx.x;
+  const int strip = unit % a.strips;
+  const int band = (unit / a.strips) % a.bands;
+  const int frame = unit / (a.strips * a.bands);
+  const int g = KLT_USEFUL * strip - 4 + 4 * lane;
+  const bool inimg = g >= 0 && g < a.w;
+  const bool ledge = g == 0, redge = g == a.w - 4;
+  const bool useful = inimg && lane >= 1 && lane <= 30;
+  const int r0 = band * a.band_rows, r1 = min(r0 + a.band_rows, a.h);
+  const float k3 = 3.f / 32.f, k10 = 10.f / 32.f;
+
+  const uint8_t* bgr_px = a.bgr + (size_t)frame * a.frame_stride + 3 * (size_t)max(g, 0);
+  const long long plane_off = (long long)(a.first + frame) * a.out0_fs + max(g, 0);
+  float *o_img = a.out0 + plane_off, *o_gx = a.out_gx + plane_off, *o_gy = a.out_gy + plane_off;
+
+  __shared__ __align__(16) unsigned char ring[RING][32 * 12];
+  const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(&ring[0][lane * 12]);
+  const int src_bytes = inimg ? 4 : 0;
+  // tick t: BGR row t (reflected outside the image) arrives; output row y = t - 1 leaves
+  const int t_begin = r0 - 1, t_last = r1;
+#pragma unroll
+  for (int u = 0; u < PREFETCH; ++u) issue_row<true>(ring_addr + u * 32 * 12, a, bgr_px, nullptr, t_begin + u, src_bytes);
+
+  float4 dxw[3], smw[3];   // rows t-2..t of the horizontal difference p - m and of the horizontal smoothing 3,10,3
+  float4 gprev = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < 3; ++u) dxw[u] = smw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+  for (int tb = t_begin; tb <= t_last; tb += 30) {
+#pragma unroll
+    for (int u = 0; u < 30; ++u) {
+      const int t = tb + u;
+      asm volatile("cp.async.wait_group %0;" ::"n"(PREFETCH - 1) : "memory");
+      issue_row<true>(ring_addr + ((u + PREFETCH) % RING) * 32 * 12, a, bgr_px, nullptr, t + PREFETCH, src_bytes);
+      const uint32_t* rr = reinterpret_cast<const uint32_t*>(&ring[u % RING][lane * 12]);
+      const float4 gr = gray4(rr[0], rr[1], rr[2]);
+      float m = __shfl_up_sync(SFE_FULL, gr.w, 1), p = __shfl_down_sync(SFE_FULL, gr.x, 1);
+      if (ledge) m = gr.y;   // column -1 mirrors to 1
+      if (redge) p = gr.z;   // column w mirrors to w-2
+      dxw[u % 3] = make_float4(gr.y - m, gr.z - gr.x, gr.w - gr.y, p - gr.z);
+      smw[u % 3] = make_float4(fmaf(k10, gr.x, (m + gr.y) * k3), fmaf(k10, gr.y, (gr.x + gr.z) * k3),
+                               fmaf(k10, gr.z, (gr.y + gr.w) * k3), fmaf(k10, gr.w, (gr.z + p) * k3));
+      const float4 &d0 = dxw[(u + 1) % 3], &d1 = dxw[(u + 2) % 3], &d2 = dxw[u % 3];
+      const float4 &s0 = smw[(u + 1) % 3], &s2 = smw[u % 3];
+      const int y = t - 1;
+      if (useful && y >= r0 && y < r1) {
+        const size_t o = (size_t)y * a.out0_pitch;
+        *reinterpret_cast<float4*>(o_img + o) = gprev;
+        *reinterpret_cast<float4*>(o_gx + o) = make_float4(fmaf(k3, d0.x + d2.x, d1.x * k10), fmaf(k3, d0.y + d2.y, d1.y * k10),
+                                                           fmaf(k3, d0.z + d2.z, d1.z * k10), fmaf(k3, d0.w + d2.w, d1.w * k10));
+        *reinterpret_cast<float4*>(o_gy + o) = make_float4(s2.x - s0.x, s2.y - s0.y, s2.z - s0.z, s2.w - s0.w);
+      }
+      gprev = gr;
+    }
+  }
 }
 
 // Shared-memory accesses of the row buffers as PTX: addresses are 32-bit shared-window offsets plus immediates,
@@ -671,5 +738,39 @@ int launch_pyr_stream_down(const PyrView& v, int plane, int l, int first, int co
   if (blur_id == 1) pyr_stream_kernel<false, 0, 1><<<a.nunits, 32, 0, s>>>(a);
   else if (blur_id == 2) pyr_stream_kernel<false, 0, 2><<<a.nunits, 32, 0, s>>>(a);
   else pyr_stream_kernel<false, 0, 1, true><<<a.nunits, 32, 0, s>>>(a);
+  return 1;
+}
+
+// Level 0 of the klt.h flavour by the streaming kernel.  Returns 1 when launched, 0 when the geometry does not qualify
+// (odd widths take the Scharr row filter's scalar tail: the tiled kernel handles them).
+int launch_pyr_stream_klt_l0(const PyrView& v, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first, int count,
+                             cudaStream_t s) {
+  static const bool tiled_only = getenv("SFE_PYR_TILED") != nullptr;
+  if (tiled_only || v.w[0] % 4 != 0 || v.w[0] < 8 || v.h[0] < 2 || ((uintptr_t)bgr & 3) || row_stride % 4 || frame_stride % 4) return 0;
+  StreamArgs a{};
+  a.w = v.w[0]; a.h = v.h[0];
+  a.first = first;
+  a.bgr = bgr; a.row_stride = row_stride; a.frame_stride = frame_stride;
+  a.out0 = v.base[0][0]; a.out_gx = v.base[1][0]; a.out_gy = v.base[2][0];
+  a.out0_fs = v.frame_stride[0]; a.out0_pitch = v.pitch[0];
+  a.strips = (a.w + KLT_USEFUL - 1) / KLT_USEFUL;
+  static int slots = 0;
+  if (slots == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, klt_l0_stream_kernel, 32, 0);
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  // a band repeats two rows only, so short bands are cheap: enough units for about three waves of resident warps
+  static const double fill = getenv("SFE_KLT_L0_FILL") ? atof(getenv("SFE_KLT_L0_FILL")) : 3.0;  // experiments
+  int bands = (int)(fill * slots / ((double)count * a.strips) + 0.5);
+  const int max_bands = a.h / 16 > 0 ? a.h / 16 : 1;
+  if (bands < 1) bands = 1;
+  if (bands > max_bands) bands = max_bands;
+  a.band_rows = (a.h + bands - 1) / bands;
+  a.bands = (a.h + a.band_rows - 1) / a.band_rows;
+  a.nunits = count * a.strips * a.bands;
+  klt_l0_stream_kernel<<<a.nunits, 32, 0, s>>>(a);
   return 1;
 }

@@ -112,6 +112,8 @@ int launch_pyr_build(const PyrView& v, int flavor, const uint8_t* bgr, size_t ro
                      size_t frame_stride, int first, int count, cudaStream_t s);
 int launch_pyr_stream_hessian(const PyrView& v, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first,
                               int count, cudaStream_t s, int* launches);
+int launch_pyr_stream_klt_l0(const PyrView& v, const uint8_t* bgr, size_t row_stride, size_t frame_stride, int first, int count,
+                             cudaStream_t s);
 int launch_pyr_stream_down(const PyrView& v, int plane, int l, int first, int count, int blur_id, float scale, cudaStream_t s);
 int launch_track_hessian(const PyrView& from, const PyrView& to, const TrackArgs& a,
                          const float* mask, int* counter, int num_sms, cudaStream_t s);
