@@ -206,6 +206,12 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the front-end has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one rank per GPU on a multi-socket box: stay on the CPUs next to this rank's GPU, so that the pinned buffers below
+    # are first-touched on its NUMA node and the uploads do not cross the socket interconnect (SFE_BENCH_NUMA=0: off).
+    # At N = 1 the process keeps all host threads (the cpu_baseline leg uses them).
+    numa_cpus = 0
+    if world > 1 and os.environ.get("SFE_BENCH_NUMA", "1") != "0":
+        numa_cpus = sfe.bind_host_to_device(local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -396,7 +402,8 @@ def run_gpu(args):
                         SEQ_STRIDE, nfr, B),
                     # what each rank's host link actually carried: tells a PCIe limit from a host-DRAM limit as N grows
                     "h2d_gbs_per_rank": h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9,
-                    "accepted_frac": e2e_accept},
+                    "accepted_frac": e2e_accept,
+                    "host_cpus_bound_rank0": numa_cpus},   # sfe_bind_host_to_device (N > 1): CPUs next to the rank's GPU, 0 = unbound
             # dominant kernel: track_fb_kernel (one launch per step).  It is bound by instruction issue, not by HBM: a
             # pyramid pair is read once (DRAM traffic ~ the algorithmic bytes, <1 % of the HBM peak) and then lives in
             # L1/L2.  achieved = executed warp-instructions per Newton step (ncu capture of THIS build,

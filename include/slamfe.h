@@ -256,6 +256,14 @@ int sfe_replay_sequence_yuyv(sfe_ctx* ctx, int w, int h, int depth, int nframes,
  * binds to spread a replay or a large match over the GPUs of a box.  NCCL (libnccl.so.2) is loaded at run time;
  * the collectives run on the context's stream, ordered with the kernels. */
 
+/* One process per GPU on a multi-socket box: binds the calling thread (and the threads it creates afterwards) to the CPUs
+ * next to `device` (NVML's nvmlDeviceGetCpuAffinity, else sysfs local_cpulist), intersected with the affinity it already
+ * has.  Call it before allocating pinned host buffers: first-touch then places them on the device's NUMA node, and uploads
+ * do not cross the socket interconnect (the reference is a single process on a single-socket robot and has no
+ * counterpart; bench.py --gpus N > 1 calls it).  Returns the number of CPUs bound to, 0 when nothing was changed (no
+ * topology information, or the intersection is empty); never an error. */
+int sfe_bind_host_to_device(int device);
+
 /* Contiguous block [lo, hi) of n units owned by `rank` of `world` (blocks differ by at most one unit). */
 int sfe_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
 /* Communicator set-up: rank 0 obtains an id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by any

@@ -39,7 +39,7 @@ EXPORTS = [
     "sfe_match_hamming256_async", "sfe_hamming_impl", "sfe_replay_pairs", "sfe_replay_sequence", "sfe_replay_sequence_yuyv", "sfe_good_features",
     "sfe_good_features_dev",
     "sfe_seed_features", "sfe_seed_features_dev", "sfe_yuyv_to_bgr", "sfe_yuyv_to_bgr_dev",
-    "sfe_shard_range", "sfe_dist_unique_id", "sfe_dist_init", "sfe_dist_attach", "sfe_dist_shutdown", "sfe_allgather_rows_dev",
+    "sfe_shard_range", "sfe_bind_host_to_device", "sfe_dist_unique_id", "sfe_dist_init", "sfe_dist_attach", "sfe_dist_shutdown", "sfe_allgather_rows_dev",
     "sfe_match_hamming256_sharded_dev", "sfe_match_hamming256_sharded",
 ]
 
@@ -92,6 +92,7 @@ def lib():
     L.sfe_host_free.argtypes = [vp, vp]
     L.sfe_launch_count.argtypes = [vp]
     L.sfe_hamming_impl.argtypes = [i32]
+    L.sfe_bind_host_to_device.argtypes = [i32]
     L.sfe_launch_count.restype = C.c_int64
     L.sfe_pyr_create.argtypes = [vp, i32, i32, i32, i32, i32, vpp]
     L.sfe_pyr_destroy.argtypes = [vp]
@@ -163,6 +164,12 @@ def _ptr(x):
 
 def _np(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def bind_host_to_device(device):
+    """sfe_bind_host_to_device: bind this process to the CPUs next to `device` (before allocating pinned buffers).
+    Returns the number of CPUs bound to, 0 when nothing changed."""
+    return int(lib().sfe_bind_host_to_device(int(device)))
 
 
 class FrontEnd:

@@ -13,7 +13,9 @@
 // synchronisation.  NCCL is resolved at run time from libnccl.so.2 (the copy the process already loaded, e.g.
 // PyTorch's, else the system's): libslamfe.so itself has no link-time dependency on it and every other entry
 // works without it.
+#include <ctype.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>  // types and enums only; the functions are looked up with dlsym
 #include <stdio.h>
 #include <string.h>
@@ -130,7 +132,63 @@ void sfe_dist_release(sfe_ctx* ctx) {
   ctx->dist = nullptr;
 }
 
+namespace {
+// CPUs close to a device, as NVML reports them (nvmlDeviceGetCpuAffinity; libnvidia-ml is loaded at run time) or, when
+// NVML is not there, as sysfs does (/sys/bus/pci/devices/<id>/local_cpulist).  Returns the number of CPUs found.
+int device_cpus(int device, cpu_set_t* out) {
+  CPU_ZERO(out);
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) return 0;
+  void* h = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+  if (h) {
+    typedef int (*init_t)(void);
+    typedef int (*byid_t)(const char*, void**);
+    typedef int (*aff_t)(void*, unsigned, unsigned long*);
+    init_t init = (init_t)dlsym(h, "nvmlInit_v2");
+    byid_t byid = (byid_t)dlsym(h, "nvmlDeviceGetHandleByPciBusId_v2");
+    aff_t aff = (aff_t)dlsym(h, "nvmlDeviceGetCpuAffinity");
+    void* dev = nullptr;
+    unsigned long words[CPU_SETSIZE / (8 * sizeof(unsigned long))] = {0};
+    const unsigned nwords = (unsigned)(sizeof(words) / sizeof(words[0]));
+    if (init && byid && aff && init() == 0 && byid(bus, &dev) == 0 && aff(dev, nwords, words) == 0)
+      for (unsigned c = 0; c < CPU_SETSIZE; ++c)
+        if (words[c / (8 * sizeof(unsigned long))] >> (c % (8 * sizeof(unsigned long))) & 1ul) CPU_SET(c, out);
+  }
+  if (CPU_COUNT(out) == 0) {
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (f) {  // "0-31,64-95"
+      int lo, hi;
+      while (fscanf(f, "%d", &lo) == 1) {
+        hi = lo;
+        int ch = fgetc(f);
+        if (ch == '-') {
+          if (fscanf(f, "%d", &hi) != 1) break;
+          ch = fgetc(f);
+        }
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) CPU_SET(c, out);
+        if (ch != ',') break;
+      }
+      fclose(f);
+    }
+  }
+  return CPU_COUNT(out);
+}
+}  // namespace
+
 extern "C" {
+
+int sfe_bind_host_to_device(int device) {
+  cpu_set_t near, cur, both;
+  if (device_cpus(device, &near) == 0) return 0;
+  if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 0;
+  CPU_AND(&both, &near, &cur);  // never widen what the caller (a cpuset, taskset) allowed
+  const int n = CPU_COUNT(&both);
+  if (n == 0 || sched_setaffinity(0, sizeof(both), &both) != 0) return 0;
+  return n;
+}
 
 int sfe_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi) {
   if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return SFE_ERR_INVALID;

@@ -47,3 +47,16 @@ def test_sharded_match_cpp_threads(tmp_path, sfe, world):
                            "-L" + csrc, "-lslamfe", "-Wl,-rpath," + csrc])
     r = subprocess.run([exe, str(world), "30011", "70001"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "sharded_mismatching_ranks 0" in r.stdout, r.stdout
+
+
+def test_bind_host_to_device_only_narrows(sfe):
+    """sfe_bind_host_to_device: the process ends up on a non-empty subset of the CPUs it was allowed before (the CPUs
+    next to the GPU), or nothing changes and 0 is returned; the affinity is restored for the rest of the suite."""
+    before = os.sched_getaffinity(0)
+    try:
+        n = sfe.bind_host_to_device(0)
+        after = os.sched_getaffinity(0)
+        assert after <= before and len(after) > 0
+        assert n == 0 and after == before or n == len(after)
+    finally:
+        os.sched_setaffinity(0, before)

@@ -387,6 +387,14 @@ def test_library_builds_and_exports_every_symbol(sfe):
     assert "sm_100a" in out, "library must carry sm_100a code"
 
 
+def test_bind_host_to_device_without_gpu_is_a_no_op(sfe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by tests/test_gpu_dist.py on a GPU box")
+    before = os.sched_getaffinity(0)
+    assert sfe.bind_host_to_device(0) == 0 and os.sched_getaffinity(0) == before
+
+
 def test_no_cpu_fallback(sfe):
     import torch
     if torch.cuda.is_available():
