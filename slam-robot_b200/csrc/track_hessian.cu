@@ -46,7 +46,7 @@ struct WarpScratch {
   float tile[16 * TS];
   float zero[TS + 2];                // must directly follow tile
   float pad[32 - (TS + 2) % 32];
-  float v[6 * SFE_SLOTS * 32];       // general route: patch value of shift s, slot k, lane l at [(s*6+k)*32 + l]
+  float2 v2[3 * SFE_SLOTS * 32];     // non-fast routes: patch values of the shift pair (2p, 2p+1), slot k, lane l at [(p*6+k)*32 + l]
   float T[SFE_SLOTS * 32];           // template patch and its effective mask, slot k of lane l at [k*32 + l]
   float mkT[SFE_SLOTS * 32];
   // transposing reductions: lane l parks partial sum j at [j * RS + l]; rows 6, 7, 14, 15 of the statistics block and
@@ -124,7 +124,7 @@ __device__ __forceinline__ int gi(float f) { return __float_as_int(f); }
 // cv::getRectSubPix's border rules per pixel.  "full" 4-tap, "vertical" 2-tap (overflow column, and
 // corners), "horizontal" 2-tap (overflow row): with the unused taps zeroed and A1' = xin ? 1-a : 1,
 // B1' = vert ? 1-b : 1 the weights (A1'B1', aB1', A1'b, ab) reproduce the rule exactly (x*1 is exact
-// and a zero tap adds an exact zero), so one FMA chain serves all pixels.  Results go to S.v.
+// and a zero tap adds an exact zero), so one FMA chain serves all pixels.  Results go to S.v2.
 __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im, int ox, int oy,
                                                int nshift, bool shared_geom, int lane, const PixPack& pix) {
   int toff[SFE_SLOTS];
@@ -161,7 +161,8 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
       const float t00 = t[0], t01 = __uint_as_float(r01 & mx[k]);
       const float t10 = __uint_as_float(r10 & mv[k]), t11 = __uint_as_float(r11 & mx[k] & mv[k]);
       const float A1 = __uint_as_float((ax1 & mx[k]) | (one & ~mx[k])), B1 = __uint_as_float((ay1 & mv[k]) | (one & ~mv[k]));
-      S.v[(s * SFE_SLOTS + k) * 32 + lane] = fmaf(t11, axf * ayf, fmaf(t10, A1 * ayf, fmaf(t01, axf * B1, t00 * (A1 * B1))));
+      reinterpret_cast<float*>(S.v2)[((s >> 1) * SFE_SLOTS + k) * 64 + 2 * lane + (s & 1)] =
+          fmaf(t11, axf * ayf, fmaf(t10, A1 * ayf, fmaf(t01, axf * B1, t00 * (A1 * B1))));
     }
   }
 }
@@ -184,6 +185,16 @@ __device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgV
     ay[j] = G.y[j].x;
     ay1[j] = __float_as_uint(G.y[j].y);
   }
+  // the shifts are evaluated as pairs (2p, 2p+1) with packed FP32 (each half rounds like the scalar form); the a*b
+  // weight of a pair does not depend on the pixel
+  float2 axp[3], ayp[3], w3p[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const int jxa = (SXP >> (4 * p)) & 3, jya = (SYP >> (4 * p)) & 3, jxb = (SXP >> (4 * p + 2)) & 3, jyb = (SYP >> (4 * p + 2)) & 3;
+    axp[p] = make_float2(ax[jxa], ax[jxb]);
+    ayp[p] = make_float2(ay[jya], ay[jyb]);
+    w3p[p] = mul2(axp[p], ayp[p]);
+  }
   const unsigned one = 0x3f800000u;
 #pragma unroll 1
   for (int k = 0; k < SFE_SLOTS; ++k) {
@@ -203,19 +214,20 @@ __device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgV
       A1[j] = __uint_as_float((ax1[j] & mx) | (one & ~mx));
       B1[j] = __uint_as_float((ay1[j] & mv) | (one & ~mv));
     }
-    float* out = S.v + k * 32 + lane;
+    float2* out = S.v2 + k * 32 + lane;
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      if (s == 1 && nshift == 1) break;   // template patch: shift 0 only
-      const int jx = (SXP >> (2 * s)) & 3, jy = (SYP >> (2 * s)) & 3;
-      out[s * SFE_SLOTS * 32] = fmaf(t11, ax[jx] * ay[jy], fmaf(t10, A1[jx] * ay[jy], fmaf(t01, ax[jx] * B1[jy], t00 * (A1[jx] * B1[jy]))));
+    for (int p = 0; p < 3; ++p) {
+      if (p == 1 && nshift == 1) break;   // template patch: shift 0 only (the pair's other half is not read)
+      const int jxa = (SXP >> (4 * p)) & 3, jya = (SYP >> (4 * p)) & 3, jxb = (SXP >> (4 * p + 2)) & 3, jyb = (SYP >> (4 * p + 2)) & 3;
+      const float2 A1p = make_float2(A1[jxa], A1[jxb]), B1p = make_float2(B1[jya], B1[jyb]);
+      out[p * SFE_SLOTS * 32] = fma2(both(t11), w3p[p], fma2(both(t10), mul2(A1p, ayp[p]), fma2(both(t01), mul2(axp[p], B1p), mul2(both(t00), mul2(A1p, B1p)))));
     }
   }
 }
 
 // Plain route: no border rule and no clipping.  A compact runtime loop re-reads the 4 taps per shift, so it
 // also serves steps in which a +-h shift crosses an integer boundary (the shifts do not share their taps
-// then), template patches (one shift) and footprints that contain a zero.  Results go to S.v.
+// then), template patches (one shift) and footprints that contain a zero.  Results go to S.v2.
 __device__ __forceinline__ void straddle_sample(WarpScratch& S, int ox, int oy, int nshift, int lane,
                                                 const PixPack& pix) {
   int poff[SFE_SLOTS];
@@ -229,10 +241,11 @@ __device__ __forceinline__ void straddle_sample(WarpScratch& S, int ox, int oy, 
     const float ax = gx.x, ax1 = gx.y;
     const float ay = gy.x, ay1 = gy.y;
     const float w0 = ax1 * ay1, w1 = ax * ay1, w2 = ax1 * ay, w3 = ax * ay;
+    float* out = reinterpret_cast<float*>(S.v2) + (s >> 1) * SFE_SLOTS * 64 + 2 * lane + (s & 1);  // half s & 1 of pair s >> 1
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {
       const float* tp = S.tile + (poff[k] >= 0 ? base + poff[k] : ZOFF);
-      S.v[(s * SFE_SLOTS + k) * 32 + lane] = fmaf(tp[TS + 1], w3, fmaf(tp[TS], w2, fmaf(tp[1], w1, tp[0] * w0)));
+      out[k * 64] = fmaf(tp[TS + 1], w3, fmaf(tp[TS], w2, fmaf(tp[1], w1, tp[0] * w0)));
     }
   }
 }
@@ -400,7 +413,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     float sm = 0.f, sq = 0.f;
 #pragma unroll
     for (int k = 0; k < SFE_SLOTS; ++k) {  // hessian.h:85-91
-      const float v = S.v[k * 32 + lane];
+      const float v = S.v2[k * 32 + lane].x;
       sm = sm + v;
       sq = fmaf(v, v, sq);
       const float m = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
@@ -450,7 +463,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
     for (int p = 0; p < 3; ++p)
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k)
-        v[p][k] = make_float2(S.v[(2 * p * SFE_SLOTS + k) * 32 + lane], S.v[((2 * p + 1) * SFE_SLOTS + k) * 32 + lane]);
+        v[p][k] = S.v2[(p * SFE_SLOTS + k) * 32 + lane];
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
@@ -506,7 +519,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
       part[2 * p + 1] = acc.y;
     }
   } else {
-    // candidate pixels may be exactly 0 (hessian.h:134 skips them): rare, so a compact rolled loop over S.v
+    // candidate pixels may be exactly 0 (hessian.h:134 skips them): rare, so a compact rolled loop over S.v2
 #pragma unroll
     for (int j = 0; j < 6; ++j) part[j] = 0.f;
 #pragma unroll 1
@@ -515,7 +528,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
-        const float vv = S.v[(s * SFE_SLOTS + k) * 32 + lane];
+        const float vv = reinterpret_cast<const float*>(S.v2)[((s >> 1) * SFE_SLOTS + k) * 64 + 2 * lane + (s & 1)];
         float diff = fmaf(-vv, alpha, T[k]) - beta;
         diff = diff * diff;
         const float q = fmaf(diff, mkT[k], p);
