@@ -642,7 +642,8 @@ void launch_row_impl(StreamArgs& a, int count, cudaStream_t s) {
   }
   const int rows = 2 * a.h1;
   static const double fill = getenv("SFE_PYR_ROW_FILL") ? atof(getenv("SFE_PYR_ROW_FILL")) : 0.;  // experiments: ctas = fill * slots
-  const int max_bands = rows / 40 > 0 ? rows / 40 : 1;
+  static const int min_band = getenv("SFE_PYR_ROW_MIN_BAND") ? atoi(getenv("SFE_PYR_ROW_MIN_BAND")) : 8;  // a live frame: many short bands (latency), the cost model keeps long ones for batches
+  const int max_bands = rows / min_band > 0 ? rows / min_band : 1;
   int bands = fill > 0. ? (int)(fill * slots / ((double)count * SEGS) + 0.5) : pick_bands(count * SEGS, slots, rows, max_bands);
   static const int forced = getenv("SFE_PYR_BANDS") ? atoi(getenv("SFE_PYR_BANDS")) : 0;
   if (forced > 0) bands = forced;
