@@ -47,8 +47,7 @@ struct WarpScratch {
   float zero[TS + 2];                // must directly follow tile
   float pad[32 - (TS + 2) % 32];
   float2 v2[3 * SFE_SLOTS * 32];     // non-fast routes: patch values of the shift pair (2p, 2p+1), slot k, lane l at [(p*6+k)*32 + l]
-  float T[SFE_SLOTS * 32];           // template patch and its effective mask, slot k of lane l at [k*32 + l]
-  float mkT[SFE_SLOTS * 32];
+  float2 TM[SFE_SLOTS * 32];         // {template patch value, its effective mask weight}, slot k of lane l at [k*32 + l]
   // transposing reductions: lane l parks partial sum j at [j * RS + l]; rows 6, 7, 14, 15 of the statistics block and
   // rows 6, 7 of the score block are never written and stay zero (they feed the idle lanes of the read-back)
   float red[16 * 36];
@@ -340,7 +339,7 @@ __device__ __forceinline__ void finite_differences(float sc, int lane, float (&d
 }
 
 // Statistics of the template patch (hessian.h:32-40).  The patch itself and its effective mask (the mask
-// weight, 0 where the template pixel is exactly 0, hessian.h:134) are parked in WarpScratch::T / mkT: they
+// weight, 0 where the template pixel is exactly 0, hessian.h:134) are parked in WarpScratch::TM: they
 // are needed only in the score loop, and keeping them out of the registers while the 36 candidate values
 // are live is worth 3 % (profiles/README.md).
 struct Tmpl {
@@ -417,8 +416,7 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
       sm = sm + v;
       sq = fmaf(v, v, sq);
       const float m = (mask && lane + 32 * k < SFE_PLEN) ? __ldg(mask + lane + 32 * k) : 0.f;
-      S.T[k * 32 + lane] = v;
-      S.mkT[k * 32 + lane] = v == 0.f ? 0.f : m;
+      S.TM[k * 32 + lane] = make_float2(v, v == 0.f ? 0.f : m);
     }
     const float red = div169(packed_reduce2(sm, sq, lane));
     t.mean = __shfl_sync(SFE_FULL, red, 0);
@@ -491,8 +489,9 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
   float T[SFE_SLOTS], mkT[SFE_SLOTS];  // parked in shared memory while the patch values occupy the registers
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k) {
-    T[k] = S.T[k * 32 + lane];
-    mkT[k] = S.mkT[k * 32 + lane];
+    const float2 tm = S.TM[k * 32 + lane];
+    T[k] = tm.x;
+    mkT[k] = tm.y;
   }
   // lanes 0, 2, .., 10 publish -alpha and -beta of shifts 0..5 ((-v)*alpha == v*(-alpha) and x - beta == x + (-beta), exactly)
   if (live && !(lane & 1)) {
@@ -662,7 +661,7 @@ __global__ void __launch_bounds__(32 * TRK_WARPS) get_patches_kernel(PyrView v, 
   evaluate(scratch[warp], tag, img_of(v, 0, level, frame), true, t, nullptr, xy[2 * i], xy[2 * i + 1], lane, make_pixpack(lane), d);
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k)
-    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = scratch[warp].T[k * 32 + lane];
+    if (lane + 32 * k < SFE_PLEN) patches[(size_t)i * SFE_PLEN + lane + 32 * k] = scratch[warp].TM[k * 32 + lane].x;
   if (lane == 0) { mean[i] = t.mean; sumsq[i] = t.sumsq; }
 }
 
