@@ -39,7 +39,13 @@ constexpr int TRK_WARPS = TRK_WARPS_D;
 #ifndef TRK_MINB
 #define TRK_MINB 4  // resident CTAs per SM the register allocator must allow (4 -> <=128 registers)
 #endif
-constexpr int TS = 16;          // tile row stride (floats)
+#ifndef TRK_TS
+#define TRK_TS 45
+#endif
+// Tile row stride (floats).  45 = 13 + 32: patch pixel i = 13 pr + pc of a slot then sits in bank (i + const) mod 32, so the
+// four tap loads of the 32 lanes are conflict-free; with a stride of 16 rows r and r + 2 share their banks and every tap load
+// takes two wavefronts (the LSU / shared-memory path is this kernel's busiest unit: 66 %, profiles/track_r2e_summary.txt).
+constexpr int TS = TRK_TS;
 constexpr int ZOFF = 16 * TS;   // taps of unused patch entries point at the zero region behind the tile
 
 struct WarpScratch {
@@ -50,8 +56,7 @@ struct WarpScratch {
   float2 TM[SFE_SLOTS * 32];         // {template patch value, its effective mask weight}, slot k of lane l at [k*32 + l]
   // transposing reductions: lane l parks partial sum j at [j * RS + l]; rows 6, 7, 14, 15 of the statistics block and
   // rows 6, 7 of the score block are never written and stay zero (they feed the idle lanes of the read-back)
-  float red[16 * 36];
-  float red2[8 * 36];
+  float red[16 * 36];                // statistics; the six scores reuse rows 0-5 (a __syncwarp apart)
   // lane-parallel results that every lane needs, handed over with one store and a few broadcast loads instead of one
   // shuffle per value: geo[j] = {a, 1-a, i0, r} of axis variant j (0..2: x, 4..6: y), ab = -alpha (0..5), -beta (8..13)
   float4 geo[8];
@@ -60,24 +65,24 @@ struct WarpScratch {
 constexpr int RS = 36;  // row stride of the reduction blocks: 16-byte aligned rows, and the float4 read-back of a quarter-warp
                         // (4 rows x 2 halves, or 2 rows x 4 quarters) touches 32 distinct banks
 
-// Per-lane patch coordinates, packed: byte k of (lo, hi) is pr * 16 + pc of the lane's slot k (i = lane + 32 k,
-// pr = i / 13, pc = i % 13) -- with the tile's row stride of 16 that byte IS the tap offset inside the footprint.
-// Two registers for the whole kernel instead of six quotients plus the multiply-subtract per slot and evaluation.
+// Per-lane tap offsets, packed: 16-bit field k of (a, b, c) is pr * TS + pc of the lane's slot k (i = lane + 32 k,
+// pr = i / 13, pc = i % 13) -- the tap offset inside the footprint.  Three registers for the whole kernel instead of six
+// quotients plus the multiply-subtract per slot and evaluation.
 struct PixPack {
-  unsigned lo, hi;
+  unsigned a, b, c;
 };
 __device__ __forceinline__ PixPack make_pixpack(int lane) {
-  PixPack p{0u, 0u};
+  unsigned w[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int k = 0; k < SFE_SLOTS; ++k) {
     const int i = lane + 32 * k;
-    const unsigned b = i < SFE_PLEN ? (unsigned)((i / SFE_PATCH) * TS + i % SFE_PATCH) : 0u;
-    if (k < 4) p.lo |= b << (8 * k); else p.hi |= b << (8 * (k - 4));
+    const unsigned f = i < SFE_PLEN ? (unsigned)((i / SFE_PATCH) * TS + i % SFE_PATCH) : 0u;
+    w[k >> 1] |= f << (16 * (k & 1));
   }
-  return p;
+  return PixPack{w[0], w[1], w[2]};
 }
-__device__ __forceinline__ int pix_off(const PixPack& p, int k) {   // zero-extended byte k: one PRMT
-  return (int)__byte_perm(k < 4 ? p.lo : p.hi, 0u, 0x4440u + (unsigned)(k & 3));
+__device__ __forceinline__ int pix_off(const PixPack& p, int k) {   // zero-extended field k: one PRMT
+  return (int)__byte_perm(k < 2 ? p.a : (k < 4 ? p.b : p.c), 0u, (k & 1) ? 0x4432u : 0x4410u);
 }
 
 // x variants live in lanes 0..2 (p, p-h, p+h), y variants in lanes 4..6; BruteHessian's shifts
@@ -138,7 +143,7 @@ __device__ __forceinline__ void general_sample(WarpScratch& S, const ImgView& im
 #pragma unroll
       for (int k = 0; k < SFE_SLOTS; ++k) {
         const int i = lane + 32 * k;
-        const int po = pix_off(pix, k), pr = po >> 4, pc = po & 15;
+        const int pr = (int)((unsigned)i / SFE_PATCH), pc = i - SFE_PATCH * pr;
         const bool valid = (k < SFE_SLOTS - 1 || i < SFE_PLEN) && pr >= ry && pc >= rx;
         const int X = x0 + pc, Y = y0 + pr;
         const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
@@ -197,8 +202,8 @@ __device__ __forceinline__ void general_sample_shared(WarpScratch& S, const ImgV
   const unsigned one = 0x3f800000u;
 #pragma unroll 1
   for (int k = 0; k < SFE_SLOTS; ++k) {
-    const int po = (int)(((k < 4 ? pix.lo : pix.hi) >> (8 * (k & 3))) & 0xffu), pr = po >> 4, pc = po & 15;
-    const bool valid = lane + 32 * k < SFE_PLEN && pr >= ry && pc >= rx;
+    const int i = lane + 32 * k, pr = (int)((unsigned)i / SFE_PATCH), pc = i - SFE_PATCH * pr;
+    const bool valid = i < SFE_PLEN && pr >= ry && pc >= rx;
     const int X = x0 + pc, Y = y0 + pr;
     const bool xin = X >= 0 && X + 1 <= im.w - 1, yin = Y >= 0 && Y + 1 <= im.h - 1;
     int Xq = X;
@@ -293,11 +298,11 @@ __device__ __forceinline__ float reduce_stats(WarpScratch& S, const float (&st)[
 }
 // 6 scores.  Returns the total of row (lane >> 2) (lanes 24-31: zero).
 __device__ __forceinline__ float reduce_scores(WarpScratch& S, const float (&part)[8], int lane) {
-  float* w = S.red2 + lane;
+  float* w = S.red + lane;
 #pragma unroll
   for (int j = 0; j < 6; ++j) w[j * RS] = part[j];
   __syncwarp();
-  const float4* r = reinterpret_cast<const float4*>(S.red2 + (lane >> 2) * RS + (lane & 3) * 8);
+  const float4* r = reinterpret_cast<const float4*>(S.red + (lane >> 2) * RS + (lane & 3) * 8);
   const float4 a = r[0], b = r[1];
   float q = tree4(a) + tree4(b);  // 8 lanes
   q = q + __shfl_xor_sync(SFE_FULL, q, 1);
@@ -543,9 +548,8 @@ __device__ __forceinline__ float evaluate(WarpScratch& S, TileTag& tag, const Im
 }
 
 __device__ __forceinline__ void init_scratch(WarpScratch& S, int lane) {
-  if (lane < TS + 2) S.zero[lane] = 0.f;
+  for (int i = lane; i < TS + 2; i += 32) S.zero[i] = 0.f;
   for (int i = lane; i < 16 * RS; i += 32) S.red[i] = 0.f;
-  for (int i = lane; i < 8 * RS; i += 32) S.red2[i] = 0.f;
   __syncwarp();
 }
 
