@@ -559,11 +559,9 @@ int launch_good_features(const uint8_t* bgr, size_t row_stride, size_t frame_str
   gftt_nms_kernel<<<dim3((w + 255) / 256, (h + NMS_ROWS - 1) / NMS_ROWS, count), 256, 0, s>>>(na);
   SelArgs sa{keys, ncand, corners, ncorners, w, cap, max_corners, min_distance};
   const size_t smem = ((sizeof(float) * 2 * (size_t)max_corners + 15) & ~(size_t)15) + sizeof(unsigned long long) * SEL_CHUNK;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr{};
+  if (first_use_on_device(attr))
     cudaFuncSetAttribute(gftt_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // + 17 KB static (histogram) stays under 227 KB
-    attr = true;
-  }
   gftt_select_kernel<<<count, SEL_THREADS, smem, s>>>(sa);
   e = cudaGetLastError();
   return e == cudaSuccess ? launches : -(int)e;

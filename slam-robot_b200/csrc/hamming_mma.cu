@@ -366,11 +366,10 @@ hamming_mma_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __res
 // (MM_PARTS * splits) or a negative cudaError.
 int launch_hamming_mma(const uint32_t* q, int nq, const uint32_t* t, int nt, int batch, int num_sms, void** ws, size_t* ws_cap,
                        cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured{};
+  if (first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(hamming_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
     if (e != cudaSuccess) return -(int)e;
-    configured = true;
   }
   const int mtiles = (nq + MM_MQ - 1) / MM_MQ;
   const int ntiles = (nt + MM_N - 1) / MM_N;

@@ -631,12 +631,14 @@ static int pick_bands(int ctas_per_band, int slots, int rows, int max_bands) {
 
 template <int NW, bool BULK, int SEGS>
 void launch_row_impl(StreamArgs& a, int count, cudaStream_t s) {
-  static int slots = 0;  // resident CTAs on the device
+  static int slots = 0;  // resident CTAs on the device (the GPUs of a box are alike)
+  static PerDeviceOnce attr{};
+  if (first_use_on_device(attr))
+    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1, BULK, SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
   if (slots == 0) {
     int dev = 0, per_sm = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(pyr_row_kernel<NW, 0, 1, BULK, SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes<NW>());
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pyr_row_kernel<NW, 0, 1, BULK, SEGS>, 32 * NW, row_smem_bytes<NW>());
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }

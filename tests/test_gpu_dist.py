@@ -45,7 +45,7 @@ def test_sharded_match_cpp_threads(tmp_path, sfe, world):
     csrc = os.path.join(ROOT, "slam-robot_b200", "csrc")
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dist.cpp"),
                            "-L" + csrc, "-lslamfe", "-Wl,-rpath," + csrc])
-    r = subprocess.run([exe, str(world), "30011", "70001"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    r = subprocess.run([exe, str(world), "30011", "70001"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0 and "sharded_mismatching_ranks 0" in r.stdout, r.stdout
 
 
