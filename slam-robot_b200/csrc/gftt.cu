@@ -17,6 +17,7 @@
 //                       minimum-distance selection, each candidate tested against the accepted corners by all
 //                       threads at once.
 #include "ctx.cuh"
+#include "device_once.cuh"
 
 namespace {
 

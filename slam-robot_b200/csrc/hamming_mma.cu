@@ -26,6 +26,7 @@
 // while the workers scan tile g-1 and unpack tile g+1, across item boundaries as well.  What bounds it is the ALU pipe
 // of the worker warps (profiles/ham_r2*): the nine UTCIMMA per tile hide completely behind unpack + scan.
 #include "sfe_common.cuh"
+#include "device_once.cuh"
 
 namespace {
 

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "pyr_math.cuh"
+#include "device_once.cuh"
 
 namespace {
 

@@ -89,21 +89,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 both(float s) { return make_float2(s, s); }
 
-// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) belong to a device, not to the process: a
-// C++ caller that drives several GPUs from one process (one sfe_ctx per GPU) needs them set on each.
-// Returns true the first time it is called for the current device with this flag array.
-struct PerDeviceOnce {
-  unsigned char seen[64];
-};
-inline bool first_use_on_device(PerDeviceOnce& o) {
-  int d = 0;
-  cudaGetDevice(&d);
-  d &= 63;
-  if (o.seen[d]) return false;
-  o.seen[d] = 1;
-  return true;
-}
-
 // ---- internal launch interface (capi.cu <-> kernels) -----------------------------------
 struct TrackArgs {
   int n, n_per_pair, from_first, to_first;
