@@ -283,7 +283,10 @@ int sfe_allgather_rows_dev(sfe_ctx* ctx, const void* local_dev, size_t row_bytes
  * on the other ranks (ncclBroadcast); idx_all / dist_all [nq_total][2] and pass_all [nq_total] (may be NULL) receive the
  * rows of ALL ranks (all-gather), identical to a single-GPU sfe_match_hamming256 of the whole problem.  The _dev
  * variant takes device pointers and only enqueues; the host variant copies in, runs, copies out and synchronises
- * (t may be NULL on ranks other than train_root). */
+ * (t may be NULL on ranks other than train_root).  Collective: every rank of the communicator must call it.  A rank
+ * whose own match cannot be launched still takes part in the all-gathers with its rows marked invalid (idx = dist = -1,
+ * pass = 0) and then returns the error, so that its peers are not left waiting; argument errors are returned before any
+ * collective is entered -- treat a non-zero return on any rank as fatal for the communicator, as with NCCL itself. */
 int sfe_match_hamming256_sharded_dev(sfe_ctx* ctx, const uint32_t* q_local, int64_t nq_total, uint32_t* t, int nt,
                                      int train_root, int ratio_num, int ratio_den, int max_dist, int32_t* idx_all,
                                      int32_t* dist_all, uint8_t* pass_all);

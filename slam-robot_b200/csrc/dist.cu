@@ -256,6 +256,7 @@ int sfe_match_hamming256_sharded_dev(sfe_ctx* ctx, const uint32_t* q_local, int6
   int64_t lo, hi;
   shard(nq_total, d->rank, d->world, &lo, &hi);
   if (hi - lo > 0x7fffffff || (hi > lo && !q_local)) return dfail(ctx, SFE_ERR_INVALID, "bad query block", nullptr);
+  int local_rc = SFE_SUCCESS;
   // 1. replicate the train set (32 B per descriptor) from the rank that owns it
   if (d->world > 1 && nt > 0) NC(nccl()->Broadcast(t, t, (size_t)nt * 32, ncclUint8, train_root, d->comm, ctx->stream));
   // 2. this rank's query rows against the whole train set, written straight into their rows of the gathered arrays
@@ -263,14 +264,22 @@ int sfe_match_hamming256_sharded_dev(sfe_ctx* ctx, const uint32_t* q_local, int6
     if (ctx->ham_pending) DCU(cudaStreamWaitEvent(ctx->stream, ctx->ham_done, 0));
     int nl = launch_hamming256(q_local, (int)(hi - lo), t, nt, 1, ratio_num, ratio_den, max_dist, idx_all + 2 * lo, dist_all + 2 * lo,
                                pass_all ? pass_all + lo : nullptr, &ctx->ham_ws, &ctx->ham_cap, ctx->stream);
-    if (nl < 0) return dfail(ctx, SFE_ERR_CUDA, "hamming launch", cudaGetErrorString((cudaError_t)(-nl)));
-    ctx->launches += nl;
+    if (nl < 0) {
+      // a rank that cannot match still enters the collectives below -- its peers would otherwise wait in the all-gather
+      // for ever -- with its rows marked invalid (idx = dist = -1, pass = 0), and reports the error when they are done
+      local_rc = dfail(ctx, SFE_ERR_CUDA, "hamming launch", cudaGetErrorString((cudaError_t)(-nl)));
+      cudaMemsetAsync(idx_all + 2 * lo, 0xff, 8 * (size_t)(hi - lo), ctx->stream);
+      cudaMemsetAsync(dist_all + 2 * lo, 0xff, 8 * (size_t)(hi - lo), ctx->stream);
+      if (pass_all) cudaMemsetAsync(pass_all + lo, 0, (size_t)(hi - lo), ctx->stream);
+    } else {
+      ctx->launches += nl;
+    }
   }
   // 3. all-gather the result rows in place
   if ((rc = gather_in_place(ctx, idx_all, 8, nq_total))) return rc;
   if ((rc = gather_in_place(ctx, dist_all, 8, nq_total))) return rc;
   if (pass_all && (rc = gather_in_place(ctx, pass_all, 1, nq_total))) return rc;
-  return SFE_SUCCESS;
+  return local_rc;
 }
 
 int sfe_match_hamming256_sharded(sfe_ctx* ctx, const uint32_t* q_local, int64_t nq_total, const uint32_t* t, int nt,
