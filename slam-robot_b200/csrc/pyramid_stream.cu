@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(32) pyr_stream_kernel(const StreamArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Row-CTA variant of the fused level-0 + level-1 kernel, for widths of NW * 128 columns.
+// Row-CTA variant of the fused level-0 + level-1 kernel, for widths of NW * 128 columns (SEGS = 1) or for wider rows cut
+// into SEGS column segments with halo lanes (1920 columns = 4 segments of a 4-warp CTA).
 //
 // The strip kernel above spends 4 of its 32 lanes per warp on halo columns and (at 640 columns) rounds 5.7 strips
 // up to 6: 768 lane-columns work for 640 image columns.  Here a CTA owns the FULL width of a row band -- warp k
