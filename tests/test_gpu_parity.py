@@ -611,3 +611,24 @@ def test_yuyv_to_bgr_bit_exact(fe, po):
     buf[:16] = [0, 0, 0, 0, 255, 255, 255, 255, 255, 0, 255, 0, 0, 255, 0, 255]
     assert np.array_equal(fe.yuyv_to_bgr(buf), po.yuyv_to_bgr(buf))
     assert fe.yuyv_to_bgr(np.zeros(0, np.uint8)).size == 0
+
+
+@pytest.mark.parametrize("shape,pad", [((96, 640), 4), ((60, 1920), 4), ((48, 1280), 12), ((40, 640), 1), ((64, 1920), 16)])
+def test_pyramid_device_frames_with_row_padding(fe, po, synth, shape, pad):
+    """sfe_pyr_build_dev on caller-owned device frames whose rows are padded: a stride that is a multiple of 4 but not of
+    16 takes the row kernel's per-lane cp.async ring instead of the bulk copies (640 / 1280 columns, and the four column
+    segments of 1920), a multiple of 16 the bulk copies with a non-dense stride, an odd stride the tiled kernels."""
+    import torch
+    H, W = shape
+    frames = synth.make_frames(31, 2, H, W)
+    stride = W * 3 + pad
+    buf = torch.zeros((2, H, stride), dtype=torch.uint8, device="cuda")
+    buf[:, :, :W * 3] = frames.reshape(2, H, W * 3).cuda()
+    torch.cuda.synchronize()
+    gp = fe.pyramid(W, H, 3, 0, 2)
+    assert fe.L.sfe_pyr_build_dev(fe.h, gp.h, buf.data_ptr(), stride, stride * H, 0, 2) == 0
+    fe.sync()
+    for f in range(2):
+        op = po.Pyramid(frames[f].numpy(), 3, 0)
+        for l in range(3):
+            assert_bits_equal(gp.plane(l, f), op.plane(l), "%dx%d pad %d frame %d level %d" % (W, H, pad, f, l))
