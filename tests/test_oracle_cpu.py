@@ -387,6 +387,16 @@ def test_library_builds_and_exports_every_symbol(sfe):
     assert "sm_100a" in out, "library must carry sm_100a code"
 
 
+@pytest.mark.parametrize("src", ["tests/cpp/test_shim.cpp", "tests/cpp/test_dist.cpp", "tools/replay_dir.cpp"])
+def test_cpp_host_layer_compiles_and_links(tmp_path, sfe, src):
+    """The reference-side C++ callers (the GpuTracker / MatcherT mirror of host/*.hpp, the multi-GPU example, the replay
+    tool) build against include/slamfe.h and link against libslamfe.so without a GPU; the GPU suite runs them."""
+    sfe.build()
+    csrc = os.path.join(ROOT, "slam-robot_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-pthread", "-o", str(tmp_path / "exe"), os.path.join(ROOT, src),
+                           "-L" + csrc, "-lslamfe", "-Wl,-rpath," + csrc])
+
+
 def test_bind_host_to_device_without_gpu_is_a_no_op(sfe):
     import torch
     if torch.cuda.is_available():
